@@ -1,0 +1,126 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (read-only checkout, build
+container only) on the seeded edge-case inputs of tests/cases.py.
+
+    python tests/golden/make_golden.py          # rewrites tests/golden/filters.npz, select.npz
+
+Stored per filter class: the input image, the raw FC features, the regressed parameters
+(``filter_param_regressor``), ``process()`` output (== ``run()``), the clipped ``forward()`` output, and
+the autograd gradients of sum(g * out) w.r.t. parameters and image for both variants.
+For the selection logic: pdf / noise / states -> pdf_sample ids, one_hot, and Agent.forward's
+new_states for a seeded Agent (states only; the nets' weights are not stored).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from tests import ref_shim, cases  # noqa: E402
+from oracle import isp_oracle as O  # noqa: E402
+
+torch.set_num_threads(1)  # fixed reduction order for the stored reference values
+
+
+def ref_class(ref, op):
+    F = ref.filters
+    return {
+        O.OP_EXPOSURE: F.ExposureFilter, O.OP_GAMMA: F.GammaFilter, O.OP_CCM: F.CCMFilter,
+        O.OP_SHARPEN: F.SharpenFilter, O.OP_NLM: F.DenoiseFilter, O.OP_TONE: F.ToneFilter,
+        O.OP_CONTRAST: F.ContrastFilter, O.OP_SATPLUS: F.SaturationPlusFilter, O.OP_WNB: F.WNBFilter,
+        O.OP_WB: F.ImprovedWhiteBalanceFilter, O.OP_USM: F.SharpenUSMFilter, O.OP_COLOR: F.ColorFilter,
+        O.OP_SHARPEN_V2: F.SharpenFilterV2,
+    }[op]
+
+
+def filters_golden(ref):
+    out = {}
+    for op in cases.ALL_OPS:
+        name = O.OP_NAMES[op]
+        flt = ref_class(ref, op)(ref.cfg, predict=False)
+        for variant, (B, H, W, seed) in {"a": (3, 20, 24, 0), "b": (1, 13, 17, 1)}.items():
+            img = cases.edge_image(B, H, W, seed)
+            feat, _ = cases.params_for(op, B, seed)
+            g = cases.grad_out(img.shape, seed)
+            key = f"{name}.{variant}"
+            out[key + ".img"] = img.numpy()
+            out[key + ".feat"] = feat.numpy()
+            out[key + ".g"] = g.numpy()
+            # regressor as the reference computes it, from the same (possibly biased) features
+            param = flt.filter_param_regressor(feat.clone())
+            out[key + ".param"] = param.detach().numpy()
+            for mode in ("run", "fwd"):
+                x = img.clone().requires_grad_(True)
+                p = param.detach().clone().requires_grad_(True)
+                if mode == "run":
+                    y = flt.run(x, p)
+                else:
+                    y, _, _ = flt.forward(x, specified_parameter=p)
+                (y * g).sum().backward()
+                out[f"{key}.{mode}.out"] = y.detach().numpy()
+                out[f"{key}.{mode}.gparam"] = p.grad.numpy()
+                out[f"{key}.{mode}.gimg"] = x.grad.numpy()
+    # known-answer vector from SURVEY.md §8a: gray pixel through S+ gets tinted
+    flt = ref.filters.SaturationPlusFilter(ref.cfg)
+    kat = flt.process(torch.full((1, 3, 1, 1), 0.25), torch.tensor([[0.5]]))
+    out["S+.kat.out"] = kat.numpy()
+    return out
+
+
+def select_golden(ref):
+    out = {}
+    A = ref.agent
+    g = torch.Generator().manual_seed(77)
+    B, n = 64, 10
+    logits = torch.randn((B, n), generator=g) * 2.0
+    u = torch.rand((B, 1), generator=g)
+    u[0, 0] = 0.0
+    u[1, 0] = 1.0
+    pdf = torch.softmax(logits, dim=1) + 1e-37
+    pdf = pdf * (1 - 0.05) + 0.05 * 1.0 / n
+    pdf = pdf / (torch.sum(pdf, dim=1, keepdim=True) + 1e-30)
+    ids = A.pdf_sample(pdf, u)
+    out["logits"], out["u"], out["pdf"] = logits.numpy(), u.numpy(), pdf.numpy()
+    out["ids_sample"] = ids.numpy()
+    out["ids_argmax"] = torch.argmax(pdf, dim=1).to(torch.int32).numpy()
+    out["one_hot"] = A.one_hot(n, ids.to(torch.int64)).numpy()
+
+    # a live Agent.forward on tiny frames: states -> new_states / ids bookkeeping
+    torch.manual_seed(5)
+    agent = A.Agent(ref.cfg, shape=(16, 64, 64), device="cpu")
+    Bs = 6
+    x = cases.edge_image(Bs, 64, 64, seed=3, in_range=True)
+    z = torch.rand((Bs, ref.cfg.z_dim), generator=g)
+    states = torch.zeros((Bs, ref.cfg.num_state_dim))
+    states[:, 2] = torch.tensor([0, 1, 2, 3, 4, 4.0])
+    states[1, 3 + 2] = 1.0
+    states[3, 3:] = 1.0
+    for mode in ("train", "eval"):
+        agent.train(mode == "train")
+        torch.manual_seed(9)
+        with torch.no_grad():
+            (xo, new_states, surrogate, penalty), dbg, _ = agent((x, z, states), 0.3)
+        sel = dbg["selected_filter"]
+        out[f"agent.{mode}.x"] = x.numpy()
+        out[f"agent.{mode}.u"] = z[:, 0:1].numpy()
+        out[f"agent.{mode}.states"] = states.numpy()
+        out[f"agent.{mode}.selected"] = sel.numpy()
+        out[f"agent.{mode}.new_states"] = new_states.numpy()
+    return out
+
+
+def main():
+    ref = ref_shim.load()
+    f = filters_golden(ref)
+    np.savez_compressed(os.path.join(HERE, "filters.npz"), **f)
+    s = select_golden(ref)
+    np.savez_compressed(os.path.join(HERE, "select.npz"), **s)
+    for fn in ("filters.npz", "select.npz"):
+        print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")
+
+
+if __name__ == "__main__":
+    main()
