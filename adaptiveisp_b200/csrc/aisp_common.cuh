@@ -1,0 +1,210 @@
+// Shared device-side vocabulary of the sm_100a ISP kernels: op classification, per-step derived
+// constants, streaming 128-bit loads/stores and the block-level gradient reduction.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/aisp_b200.h"
+
+#define AISP_LN2F 0.69314718055994530942f
+#define AISP_PIF 3.14159265358979323846f
+
+namespace aisp {
+
+constexpr int kThreads = 256;          // every kernel here runs 8 warps per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr int kConst = 32;             // floats of derived constants per step (>= AISP_PSTRIDE + 3)
+
+__host__ __device__ __forceinline__ bool is_pointwise(int op) {
+    return op == AISP_OP_EXPOSURE || op == AISP_OP_GAMMA || op == AISP_OP_CCM || op == AISP_OP_TONE ||
+           op == AISP_OP_CONTRAST || op == AISP_OP_SATPLUS || op == AISP_OP_WNB || op == AISP_OP_WB ||
+           op == AISP_OP_COLOR;
+}
+__host__ __device__ __forceinline__ bool is_sharpen(int op) {
+    return op == AISP_OP_SHARPEN || op == AISP_OP_SHARPEN_V2 || op == AISP_OP_USM;
+}
+
+// ---------------------------------------------------------------------------------------------
+// streaming global access: every image byte is touched once per pass, so bypass L1 allocation
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream1(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream4(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void stg_stream1(float* p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+template <int VEC>
+struct Pack;
+template <>
+struct Pack<4> {
+    float v[4];
+    __device__ __forceinline__ void load(const float* p) {
+        float4 t = ldg_stream4(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ void store(float* p) const { stg_stream4(p, make_float4(v[0], v[1], v[2], v[3])); }
+};
+template <>
+struct Pack<1> {
+    float v[1];
+    __device__ __forceinline__ void load(const float* p) { v[0] = ldg_stream1(p); }
+    __device__ __forceinline__ void store(float* p) const { stg_stream1(p, v[0]); }
+};
+
+// torch.clip semantics: NaN stays NaN (fminf/fmaxf would swallow it)
+__device__ __forceinline__ float clip01(float y) { return y < 0.f ? 0.f : (y > 1.f ? 1.f : y); }
+// clamp backward: gradient passes iff lo <= y <= hi, inclusive (NaN -> 0)
+__device__ __forceinline__ float pass01(float y) { return (y >= 0.f && y <= 1.f) ? 1.f : 0.f; }
+
+// ---------------------------------------------------------------------------------------------
+// per-step derived constants (one thread per step computes them once per CTA / finalize block)
+//   raw : AISP_PSTRIDE parameters as the regressor produced them
+//   c   : kConst floats consumed by the per-pixel code
+// ---------------------------------------------------------------------------------------------
+__device__ inline void derive_consts(int op, const float* raw, float* c) {
+    switch (op) {
+    case AISP_OP_EXPOSURE:  // img * exp(p * ln2)            isp/filters.py:224
+        c[0] = expf(raw[0] * AISP_LN2F);
+        break;
+    case AISP_OP_CCM: {  // rows / row-sum, no epsilon        isp/filters.py:706-707
+        for (int i = 0; i < 3; ++i) {
+            float s = (raw[3 * i] + raw[3 * i + 1]) + raw[3 * i + 2];
+            for (int j = 0; j < 3; ++j) c[3 * i + j] = raw[3 * i + j] / s;
+            c[9 + i] = 1.0f / s;
+        }
+        break;
+    }
+    case AISP_OP_TONE: {  // steps / (sum + 1e-30)            isp/filters.py:340,345
+        float s = 0.f;
+        for (int k = 0; k < 8; ++k) { c[k] = raw[k]; s += raw[k]; }
+        c[8] = 8.0f / (s + 1e-30f);
+        break;
+    }
+    case AISP_OP_COLOR: {  // per-channel curves              isp/filters.py:297,302
+        float s[3] = {0.f, 0.f, 0.f};
+        for (int k = 0; k < 8; ++k)
+            for (int ch = 0; ch < 3; ++ch) { c[3 * k + ch] = raw[3 * k + ch]; s[ch] += raw[3 * k + ch]; }
+        for (int ch = 0; ch < 3; ++ch) c[24 + ch] = 8.0f / (s[ch] + 1e-30f);
+        break;
+    }
+    case AISP_OP_USM: {  // 5-tap gaussian and its sigma-derivative   isp/sharpen.py:15-23
+        float sigma = raw[0];
+        float e[5], sum = 0.f, m2 = 0.f;
+        for (int i = 0; i < 5; ++i) {
+            float x = (float)(i - 2);
+            float t = x / sigma;
+            e[i] = expf(-0.5f * (t * t));
+            sum += e[i];
+        }
+        for (int i = 0; i < 5; ++i) { c[i] = e[i] / sum; }
+        for (int i = 0; i < 5; ++i) { float x = (float)(i - 2); m2 += c[i] * x * x; }
+        float inv3 = 1.0f / (sigma * sigma * sigma);
+        for (int i = 0; i < 5; ++i) { float x = (float)(i - 2); c[5 + i] = c[i] * (x * x - m2) * inv3; }
+        c[10] = raw[1];  // amount
+        break;
+    }
+    default:  // E handled above; G, W, Ct, S+, BW, Shr, ShrV2, NLM use the raw values
+        for (int k = 0; k < 3; ++k) c[k] = raw[k];
+        break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// raw per-sample partial sums -> parameter gradients (chain rule through the derived constants)
+//   a : AISP_ACC_STRIDE reduced accumulators (double), c : derived constants, gp : PSTRIDE outputs
+// ---------------------------------------------------------------------------------------------
+__device__ inline void finalize_grads(int op, const double* a, const float* c, const float* raw, float* gp) {
+    for (int k = 0; k < AISP_PSTRIDE; ++k) gp[k] = 0.f;
+    switch (op) {
+    case AISP_OP_EXPOSURE:  // a0 = sum gy*x ; dy/dp = x * 2^p * ln2
+        gp[0] = (float)(a[0] * (double)c[0] * (double)AISP_LN2F);
+        break;
+    case AISP_OP_GAMMA:  // a0 = sum gy*y*log2(max(x,.001))
+        gp[0] = (float)(a[0] * (double)AISP_LN2F);
+        break;
+    case AISP_OP_WB:
+        for (int k = 0; k < 3; ++k) gp[k] = (float)a[k];
+        break;
+    case AISP_OP_CCM:  // a[3i+j] = sum gy_i*x_j ; through M/rowsum
+        for (int i = 0; i < 3; ++i) {
+            double dot = a[3 * i] * c[3 * i] + a[3 * i + 1] * c[3 * i + 1] + a[3 * i + 2] * c[3 * i + 2];
+            for (int k = 0; k < 3; ++k) gp[3 * i + k] = (float)((a[3 * i + k] - dot) * (double)c[9 + i]);
+        }
+        break;
+    case AISP_OP_TONE:  // a[k] = sum gy*seg_k ; a[8] = sum gy*y
+        for (int k = 0; k < 8; ++k) gp[k] = (float)((double)c[8] * (a[k] - a[8] * 0.125));
+        break;
+    case AISP_OP_COLOR:  // a[3k+ch], a[24+ch]
+        for (int k = 0; k < 8; ++k)
+            for (int ch = 0; ch < 3; ++ch)
+                gp[3 * k + ch] = (float)((double)c[24 + ch] * (a[3 * k + ch] - a[24 + ch] * 0.125));
+        break;
+    case AISP_OP_USM:  // a0 = sum gy*(d blur/d sigma), a1 = sum gy*(x - blur)
+        gp[0] = (float)(-(double)raw[1] * a[0]);
+        gp[1] = (float)a[1];
+        break;
+    default:  // Ct, S+, BW, Shr, ShrV2, NLM: a0 is the gradient
+        gp[0] = (float)a[0];
+        break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// block reduction of N per-thread partial sums -> one row of the scratch (N <= AISP_ACC_STRIDE)
+// warp shuffles first, then a fixed-order sum over the 8 warps: deterministic.
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void block_reduce_store(float (&acc)[N], float* red /*[kWarps][32]*/, float* dst) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        float v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp * AISP_ACC_STRIDE + k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < AISP_ACC_STRIDE) {
+        float s = 0.f;
+        if (threadIdx.x < N) {
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) s += red[w * AISP_ACC_STRIDE + threadIdx.x];
+        }
+        dst[threadIdx.x] = s;
+    }
+}
+
+// Second stage shared by every family: grid = B, block = kThreads.  Sums `nrows` scratch rows of
+// sample b in fp64 (fixed order), applies finalize_grads and writes grad_params[b, :].
+__global__ void finalize_kernel(const float* __restrict__ partial, int nrows, const float* __restrict__ params,
+                                const int32_t* __restrict__ ops, int family, float* __restrict__ grad_params);
+
+enum { FAMILY_POINTWISE = 0, FAMILY_SHARPEN = 1, FAMILY_NLM = 2 };
+__host__ __device__ __forceinline__ bool in_family(int op, int family) {
+    return family == FAMILY_POINTWISE ? is_pointwise(op)
+         : family == FAMILY_SHARPEN   ? is_sharpen(op)
+                                      : op == AISP_OP_NLM;
+}
+
+// launch geometry shared between kernels and aisp_bwd_scratch_bytes
+constexpr int kPwChunkPx = 4096;       // pixels per CTA in the per-pixel kernels
+constexpr int kShTileW = 128, kShTileH = 16;   // sharpen / USM tile
+constexpr int kNlmTileW = 28, kNlmTileH = 32;  // NLM tile (28 = 32 lanes - 2*2 box halo)
+
+}  // namespace aisp

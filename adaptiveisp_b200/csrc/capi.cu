@@ -1,0 +1,144 @@
+// extern "C" boundary of libaisp_b200.so: argument validation + dispatch to the kernel launchers.
+// Plain pointers and sizes only -- no torch types.  See include/aisp_b200.h for the contract.
+#include "aisp_common.cuh"
+
+namespace aisp {
+cudaError_t launch_pointwise_fwd(const float*, float*, const float*, const int32_t*, const int32_t*, int, int, int, int,
+                                 int, cudaStream_t);
+cudaError_t launch_pointwise_bwd(const float*, const float*, const float*, const int32_t*, int, int, int, int, float*,
+                                 float*, float*, cudaStream_t);
+cudaError_t launch_sharpen_fwd(const float*, float*, const float*, const int32_t*, int, int, int, cudaStream_t);
+cudaError_t launch_sharpen_bwd(const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*,
+                               float*, float*, cudaStream_t);
+cudaError_t launch_nlm_fwd(const float*, float*, const float*, const int32_t*, int, int, int, float*, cudaStream_t);
+cudaError_t launch_nlm_bwd(const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*,
+                           cudaStream_t);
+int pointwise_rows(int H, int W);
+int sharpen_rows(int H, int W);
+}  // namespace aisp
+
+using namespace aisp;
+
+namespace {
+inline bool al4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+inline int shape_ok(int B, int H, int W) {
+    // int32 pixel indexing inside a plane; gridDim.y/z limit on the batch
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    if ((long long)H * W > (1LL << 30)) return 0;
+    if (B > 65535) return 0;
+    return 1;
+}
+}  // namespace
+
+extern "C" {
+
+int aisp_version(void) { return 1; }
+
+const char* aisp_status_string(int s) {
+    switch (s) {
+    case AISP_OK: return "ok";
+    case AISP_ERR_NULL: return "required pointer is NULL";
+    case AISP_ERR_SHAPE: return "shape out of range";
+    case AISP_ERR_SCRATCH: return "scratch buffer too small";
+    case AISP_ERR_UNSUPPORTED: return "unsupported combination";
+    case AISP_ERR_ALIGN: return "pointer not 4-byte aligned";
+    default: return s > 0 ? cudaGetErrorString((cudaError_t)s) : "unknown status";
+    }
+}
+
+int aisp_op_num_params(int op) {
+    static const int n[AISP_OP_COUNT] = {1, 1, 9, 1, 1, 8, 1, 1, 1, 3, 2, 24, 1};
+    return (op >= 0 && op < AISP_OP_COUNT) ? n[op] : -1;
+}
+
+size_t aisp_bwd_scratch_bytes(int B, int H, int W) {
+    if (!shape_ok(B, H, W)) return 0;
+    const int rows = pointwise_rows(H, W) > sharpen_rows(H, W) ? pointwise_rows(H, W) : sharpen_rows(H, W);
+    return (size_t)B * rows * AISP_ACC_STRIDE * sizeof(float);
+}
+
+int aisp_pointwise_fwd(const float* img, float* out, const float* params, const int32_t* ops, const int32_t* seq_len,
+                       int B, int H, int W, int S, int clip_each, void* stream) {
+    if (!img || !out || !params || !ops) return AISP_ERR_NULL;
+    if (!shape_ok(B, H, W) || S < 1 || S > AISP_MAX_STEPS) return AISP_ERR_SHAPE;
+    if (!al4(img) || !al4(out)) return AISP_ERR_ALIGN;
+    if (img == out) return AISP_ERR_UNSUPPORTED;
+    return (int)launch_pointwise_fwd(img, out, params, ops, seq_len, B, H, W, S, clip_each ? 1 : 0,
+                                     (cudaStream_t)stream);
+}
+
+int aisp_pointwise_bwd(const float* img, const float* grad_out, const float* params, const int32_t* ops, int B, int H,
+                       int W, int clip, float* grad_params, float* grad_img, void* scratch, size_t scratch_bytes,
+                       void* stream) {
+    if (!img || !grad_out || !params || !ops || !grad_params || !scratch) return AISP_ERR_NULL;
+    if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
+    if (scratch_bytes < aisp_bwd_scratch_bytes(B, H, W)) return AISP_ERR_SCRATCH;
+    if (!al4(img) || !al4(grad_out) || !al4(grad_img)) return AISP_ERR_ALIGN;
+    return (int)launch_pointwise_bwd(img, grad_out, params, ops, B, H, W, clip ? 1 : 0, grad_params, grad_img,
+                                     (float*)scratch, (cudaStream_t)stream);
+}
+
+int aisp_sharpen_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,
+                     void* stream) {
+    if (!img || !out || !params || !ops) return AISP_ERR_NULL;
+    if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
+    if (img == out) return AISP_ERR_UNSUPPORTED;
+    return (int)launch_sharpen_fwd(img, out, params, ops, B, H, W, (cudaStream_t)stream);
+}
+
+int aisp_sharpen_bwd(const float* img, const float* grad_out, const float* params, const int32_t* ops, int B, int H,
+                     int W, float* grad_params, float* grad_img, float* gy_scratch, void* scratch,
+                     size_t scratch_bytes, void* stream) {
+    if (!img || !grad_out || !params || !ops || !grad_params || !scratch) return AISP_ERR_NULL;
+    if (grad_img && !gy_scratch) return AISP_ERR_NULL;
+    if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
+    if (scratch_bytes < aisp_bwd_scratch_bytes(B, H, W)) return AISP_ERR_SCRATCH;
+    return (int)launch_sharpen_bwd(img, grad_out, params, ops, B, H, W, grad_params, grad_img, gy_scratch,
+                                   (float*)scratch, (cudaStream_t)stream);
+}
+
+int aisp_nlm_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,
+                 float* dout_dh, void* stream) {
+    if (!img || !out || !params || !ops) return AISP_ERR_NULL;
+    if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
+    if (img == out) return AISP_ERR_UNSUPPORTED;
+    return (int)launch_nlm_fwd(img, out, params, ops, B, H, W, dout_dh, (cudaStream_t)stream);
+}
+
+int aisp_nlm_bwd(const float* grad_out, const float* dout_dh, const int32_t* ops, int B, int H, int W,
+                 float* grad_params, float* grad_img, void* scratch, size_t scratch_bytes, void* stream) {
+    if (!grad_out || !dout_dh || !ops || !grad_params || !scratch) return AISP_ERR_NULL;
+    if (grad_img) return AISP_ERR_UNSUPPORTED;
+    if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
+    if (scratch_bytes < aisp_bwd_scratch_bytes(B, H, W)) return AISP_ERR_SCRATCH;
+    return (int)launch_nlm_bwd(grad_out, dout_dh, nullptr, ops, B, H, W, grad_params, (float*)scratch,
+                               (cudaStream_t)stream);
+}
+
+int aisp_select_apply_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,
+                          int clip, float* nlm_dout_dh, void* stream) {
+    int e = aisp_pointwise_fwd(img, out, params, ops, nullptr, B, H, W, 1, clip, stream);
+    if (e) return e;
+    e = aisp_sharpen_fwd(img, out, params, ops, B, H, W, stream);
+    if (e) return e;
+    return aisp_nlm_fwd(img, out, params, ops, B, H, W, nlm_dout_dh, stream);
+}
+
+int aisp_select_apply_bwd(const float* img, const float* grad_out, const float* params, const int32_t* ops, int B,
+                          int H, int W, int clip, const float* nlm_dout_dh, float* grad_params, float* grad_img,
+                          float* gy_scratch, void* scratch, size_t scratch_bytes, void* stream) {
+    // grad_img on a heterogeneous batch would need the (unimplemented) NLM image gradient for the
+    // NLM samples; refuse rather than return partially written gradients.
+    if (grad_img && nlm_dout_dh) return AISP_ERR_UNSUPPORTED;
+    int e = aisp_pointwise_bwd(img, grad_out, params, ops, B, H, W, clip, grad_params, grad_img, scratch,
+                               scratch_bytes, stream);
+    if (e) return e;
+    e = aisp_sharpen_bwd(img, grad_out, params, ops, B, H, W, grad_params, grad_img, gy_scratch, scratch,
+                         scratch_bytes, stream);
+    if (e) return e;
+    if (nlm_dout_dh)
+        e = aisp_nlm_bwd(grad_out, nlm_dout_dh, ops, B, H, W, grad_params, nullptr, scratch, scratch_bytes, stream);
+    return e;
+}
+
+}  // extern "C"

@@ -1,0 +1,702 @@
+// Fused per-pixel ISP pass for sm_100a: exposure, gamma, white balance, CCM, tone / colour curves,
+// contrast, saturation+, desaturation -- forward over a per-sample op sequence in one pass over HBM,
+// and the single-step backward (parameter gradients always, image gradient on request).
+//
+// Layout: CTA <-> (sample b = blockIdx.y, chunk of kPwChunkPx pixels = blockIdx.x).  The op id is
+// uniform per CTA, so the `switch` never diverges.  Each thread streams 16 pixels as 3 planes x
+// 4 x 128-bit loads (12 LDG.128 in flight), computes in registers, and streams the result back.
+// HBM-bound: 24 B/px forward, 24 B/px backward (36 with grad_img).  No shared-memory staging is
+// needed for the pixels (no reuse); shared memory only holds the per-step derived constants.
+#include "aisp_common.cuh"
+
+namespace aisp {
+
+// =============================================================================================
+// per-pixel forward math (in place).  c = derived constants of this step.
+// =============================================================================================
+__device__ __forceinline__ float lum_isp(float r, float g, float b) {  // isp/filters.py:12-14
+    return (0.27f * r + 0.67f * g) + 0.06f * b;
+}
+
+__device__ __forceinline__ float curve8(float x, const float* c, int stride) {
+    // sum_k clip(x - k/8, 0, 1/8) * p_k, k ascending (isp/filters.py:342-344)
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float seg = fminf(fmaxf(x - 0.125f * (float)k, 0.f), 0.125f);
+        acc = fmaf(seg, c[k * stride], acc);
+    }
+    return acc;
+}
+
+// HSV round trip of SaturationPlusFilter (isp/filters.py:445-560) for one pixel.
+// Inputs r,g,b are already clipped to [0,1].  Outputs the "full colour" pixel and (for the
+// backward) the intermediates needed by the reverse sweep.
+struct HsvState {
+    float mx, mn, d, num, sat, m, u, s2, s, vv, f;
+    int branch;  // 0: R is max, 1: G, 2: B, -1: achromatic (hue forced to 0, no gradient)
+    int sextant;
+    bool satzero;
+};
+
+__device__ __forceinline__ void satplus_full(float r, float g, float b, float& fr, float& fg, float& fb,
+                                             HsvState& st) {
+    const float mx = fmaxf(r, fmaxf(g, b));
+    const float mn = fminf(r, fminf(g, b));
+    const float d = (mx - mn) + 1e-8f;
+    float hue = 0.f, num = 0.f;
+    int branch = -1;
+    // ordered overwrites: B first, then G, then R -> R wins ties (isp/filters.py:456-464)
+    if (b == mx) { num = r - g; hue = 4.0f + num / d; branch = 2; }
+    if (g == mx) { num = b - r; hue = 2.0f + num / d; branch = 1; }
+    if (r == mx) {
+        num = g - b;
+        float q = num / d;               // |q| <= 1, so python-style q % 6 is q or q + 6
+        hue = (q < 0.f) ? q + 6.0f : q;
+        branch = 0;
+    }
+    if (mn == mx) { hue = 0.f; branch = -1; }
+    hue = hue / 6.0f;
+    float sat = (mx - mn) / (mx + 1e-8f);
+    const bool satzero = (mx == 0.f);
+    if (satzero) sat = 0.f;
+    // enhanced saturation (isp/filters.py:552)
+    const float u = 0.5f - mx;
+    const float m = 0.5f - fabsf(u);
+    const float s2 = sat + (1.f - sat) * m * 0.8f;
+    // hsv2rgb (isp/filters.py:481-533)
+    const float h = (hue >= 1.0f) ? hue - 1.0f : hue;  // h % 1 for h in [0,1]
+    const float s = clip01(s2);
+    const float vv = clip01(mx);
+    const float h6 = h * 6.0f;
+    const float hi = floorf(h6);
+    const float f = h6 - hi;
+    const float pp = vv * (1.f - s);
+    const float qq = vv * (1.f - (f * s));
+    const float tt = vv * (1.f - ((1.f - f) * s));
+    const int sx = (int)hi;
+    switch (sx) {
+    case 0: fr = vv; fg = tt; fb = pp; break;
+    case 1: fr = qq; fg = vv; fb = pp; break;
+    case 2: fr = pp; fg = vv; fb = tt; break;
+    case 3: fr = pp; fg = qq; fb = vv; break;
+    case 4: fr = tt; fg = pp; fb = vv; break;
+    case 5: fr = vv; fg = pp; fb = qq; break;
+    default: fr = 0.f; fg = 0.f; fb = 0.f; break;
+    }
+    st.mx = mx; st.mn = mn; st.d = d; st.num = num; st.sat = sat; st.m = m; st.u = u; st.s2 = s2;
+    st.s = s; st.vv = vv; st.f = f; st.branch = branch; st.sextant = sx; st.satzero = satzero;
+}
+
+template <int NPX>
+__device__ __forceinline__ void fwd_step(int op, const float* __restrict__ c, float (&R)[NPX], float (&G)[NPX],
+                                         float (&B)[NPX]) {
+    switch (op) {
+    case AISP_OP_EXPOSURE: {
+        const float s = c[0];
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) { R[i] *= s; G[i] *= s; B[i] *= s; }
+        break;
+    }
+    case AISP_OP_GAMMA: {  // pow(max(x, 0.001), p) via lg2/ex2 (MUFU): |err| << 1e-5 on [0,1]
+        const float p = c[0];
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) {
+            R[i] = exp2f(p * __log2f(fmaxf(R[i], 0.001f)));
+            G[i] = exp2f(p * __log2f(fmaxf(G[i], 0.001f)));
+            B[i] = exp2f(p * __log2f(fmaxf(B[i], 0.001f)));
+        }
+        break;
+    }
+    case AISP_OP_WB: {
+        const float s0 = c[0], s1 = c[1], s2 = c[2];
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) { R[i] *= s0; G[i] *= s1; B[i] *= s2; }
+        break;
+    }
+    case AISP_OP_CCM: {  // out_i = sum_j M[i][j] x_j   (isp/filters.py:666-672)
+        float m[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) m[k] = c[k];
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) {
+            const float r = R[i], g = G[i], b = B[i];
+            R[i] = fmaf(b, m[2], fmaf(g, m[1], r * m[0]));
+            G[i] = fmaf(b, m[5], fmaf(g, m[4], r * m[3]));
+            B[i] = fmaf(b, m[8], fmaf(g, m[7], r * m[6]));
+        }
+        break;
+    }
+    case AISP_OP_TONE: {
+        const float sc = c[8];
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) {
+            R[i] = curve8(R[i], c, 1) * sc;
+            G[i] = curve8(G[i], c, 1) * sc;
+            B[i] = curve8(B[i], c, 1) * sc;
+        }
+        break;
+    }
+    case AISP_OP_COLOR: {
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) {
+            R[i] = curve8(R[i], c + 0, 3) * c[24];
+            G[i] = curve8(G[i], c + 1, 3) * c[25];
+            B[i] = curve8(B[i], c + 2, 3) * c[26];
+        }
+        break;
+    }
+    case AISP_OP_CONTRAST: {  // isp/filters.py:415-419
+        const float p = c[0], ip = 1.f - p;
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) {
+            const float l = clip01(lum_isp(R[i], G[i], B[i]));
+            const float cl = -__cosf(AISP_PIF * l) * 0.5f + 0.5f;
+            const float inv = 1.0f / (l + 1e-6f);
+            R[i] = ip * R[i] + p * (R[i] * inv * cl);
+            G[i] = ip * G[i] + p * (G[i] * inv * cl);
+            B[i] = ip * B[i] + p * (B[i] * inv * cl);
+        }
+        break;
+    }
+    case AISP_OP_WNB: {  // isp/filters.py:435-437
+        const float p = c[0], ip = 1.f - p;
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) {
+            const float l = lum_isp(R[i], G[i], B[i]);
+            R[i] = ip * R[i] + p * l;
+            G[i] = ip * G[i] + p * l;
+            B[i] = ip * B[i] + p * l;
+        }
+        break;
+    }
+    case AISP_OP_SATPLUS: {
+        const float p = c[0], ip = 1.f - p;
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) {
+            const float r = clip01(R[i]), g = clip01(G[i]), b = clip01(B[i]);
+            float fr, fg, fb;
+            HsvState st;
+            satplus_full(r, g, b, fr, fg, fb, st);
+            R[i] = r * ip + fr * p;
+            G[i] = g * ip + fg * p;
+            B[i] = b * ip + fb * p;
+        }
+        break;
+    }
+    default: break;
+    }
+}
+
+// =============================================================================================
+// per-pixel backward of one step.  (gr,gg,gb): upstream gradient in, image gradient out (GIMG).
+// acc: raw per-thread partial sums, turned into parameter gradients by finalize_grads().
+// =============================================================================================
+template <int OP>
+struct PwBwd;
+
+#define AISP_MASK_CLIP(yr, yg, yb)                                   \
+    if (clip) { gr *= pass01(yr); gg *= pass01(yg); gb *= pass01(yb); }
+
+template <>
+struct PwBwd<AISP_OP_EXPOSURE> {
+    static constexpr int NACC = 1;
+    template <bool GIMG>
+    static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
+                                              float& gb, int clip, float* acc) {
+        const float s = c[0];
+        AISP_MASK_CLIP(r * s, g * s, b * s)
+        acc[0] += gr * r + gg * g + gb * b;
+        if (GIMG) { gr *= s; gg *= s; gb *= s; }
+    }
+};
+
+template <>
+struct PwBwd<AISP_OP_GAMMA> {
+    static constexpr int NACC = 1;
+    template <bool GIMG>
+    static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
+                                              float& gb, int clip, float* acc) {
+        const float p = c[0];
+        const float xr = fmaxf(r, 0.001f), xg = fmaxf(g, 0.001f), xb = fmaxf(b, 0.001f);
+        const float lr = __log2f(xr), lg = __log2f(xg), lb = __log2f(xb);
+        const float yr = exp2f(p * lr), yg = exp2f(p * lg), yb = exp2f(p * lb);
+        AISP_MASK_CLIP(yr, yg, yb)
+        acc[0] += gr * yr * lr + gg * yg * lg + gb * yb * lb;  // x ln2 in finalize
+        if (GIMG) {  // p * x^(p-1), only where the min-clamp passed (x >= 0.001, inclusive)
+            gr = (r >= 0.001f) ? gr * p * __fdividef(yr, xr) : 0.f;
+            gg = (g >= 0.001f) ? gg * p * __fdividef(yg, xg) : 0.f;
+            gb = (b >= 0.001f) ? gb * p * __fdividef(yb, xb) : 0.f;
+        }
+    }
+};
+
+template <>
+struct PwBwd<AISP_OP_WB> {
+    static constexpr int NACC = 3;
+    template <bool GIMG>
+    static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
+                                              float& gb, int clip, float* acc) {
+        AISP_MASK_CLIP(r * c[0], g * c[1], b * c[2])
+        acc[0] += gr * r; acc[1] += gg * g; acc[2] += gb * b;
+        if (GIMG) { gr *= c[0]; gg *= c[1]; gb *= c[2]; }
+    }
+};
+
+template <>
+struct PwBwd<AISP_OP_CCM> {
+    static constexpr int NACC = 9;
+    template <bool GIMG>
+    static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
+                                              float& gb, int clip, float* acc) {
+        const float yr = fmaf(b, c[2], fmaf(g, c[1], r * c[0]));
+        const float yg = fmaf(b, c[5], fmaf(g, c[4], r * c[3]));
+        const float yb = fmaf(b, c[8], fmaf(g, c[7], r * c[6]));
+        AISP_MASK_CLIP(yr, yg, yb)
+        acc[0] = fmaf(gr, r, acc[0]); acc[1] = fmaf(gr, g, acc[1]); acc[2] = fmaf(gr, b, acc[2]);
+        acc[3] = fmaf(gg, r, acc[3]); acc[4] = fmaf(gg, g, acc[4]); acc[5] = fmaf(gg, b, acc[5]);
+        acc[6] = fmaf(gb, r, acc[6]); acc[7] = fmaf(gb, g, acc[7]); acc[8] = fmaf(gb, b, acc[8]);
+        if (GIMG) {  // M^T gy
+            const float xr = c[0] * gr + c[3] * gg + c[6] * gb;
+            const float xg = c[1] * gr + c[4] * gg + c[7] * gb;
+            const float xb = c[2] * gr + c[5] * gg + c[8] * gb;
+            gr = xr; gg = xg; gb = xb;
+        }
+    }
+};
+
+// one channel of a curve filter: returns y (unscaled sum), accumulates gy*seg_k, returns slope sum
+template <bool GIMG>
+__device__ __forceinline__ void curve8_bwd(float x, const float* c, int stride, float sc, float& g, int clip,
+                                           float* acc, int astride, float& yacc) {
+    float seg[8];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        seg[k] = fminf(fmaxf(x - 0.125f * (float)k, 0.f), 0.125f);
+        sum = fmaf(seg[k], c[k * stride], sum);
+    }
+    const float y = sum * sc;
+    if (clip) g *= pass01(y);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k * astride] = fmaf(g, seg[k], acc[k * astride]);
+    yacc = fmaf(g, y, yacc);
+    if (GIMG) {  // clamp backward is inclusive at both ends: on a knot two segments pass
+        float slope = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float t = x - 0.125f * (float)k;
+            slope += (t >= 0.f && t <= 0.125f) ? c[k * stride] : 0.f;
+        }
+        g = g * sc * slope;
+    }
+}
+
+template <>
+struct PwBwd<AISP_OP_TONE> {
+    static constexpr int NACC = 9;
+    template <bool GIMG>
+    static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
+                                              float& gb, int clip, float* acc) {
+        curve8_bwd<GIMG>(r, c, 1, c[8], gr, clip, acc, 1, acc[8]);
+        curve8_bwd<GIMG>(g, c, 1, c[8], gg, clip, acc, 1, acc[8]);
+        curve8_bwd<GIMG>(b, c, 1, c[8], gb, clip, acc, 1, acc[8]);
+    }
+};
+
+template <>
+struct PwBwd<AISP_OP_COLOR> {
+    static constexpr int NACC = 27;
+    template <bool GIMG>
+    static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
+                                              float& gb, int clip, float* acc) {
+        curve8_bwd<GIMG>(r, c + 0, 3, c[24], gr, clip, acc + 0, 3, acc[24]);
+        curve8_bwd<GIMG>(g, c + 1, 3, c[25], gg, clip, acc + 1, 3, acc[25]);
+        curve8_bwd<GIMG>(b, c + 2, 3, c[26], gb, clip, acc + 2, 3, acc[26]);
+    }
+};
+
+template <>
+struct PwBwd<AISP_OP_CONTRAST> {
+    static constexpr int NACC = 1;
+    template <bool GIMG>
+    static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
+                                              float& gb, int clip, float* acc) {
+        const float p = c[0], ip = 1.f - p;
+        const float l0 = lum_isp(r, g, b);
+        const float l = clip01(l0);
+        float sn, cs;
+        __sincosf(AISP_PIF * l, &sn, &cs);
+        const float cl = -cs * 0.5f + 0.5f;
+        const float den = l + 1e-6f;
+        const float inv = 1.0f / den;
+        const float cr = r * inv * cl, cg = g * inv * cl, cb = b * inv * cl;
+        AISP_MASK_CLIP(ip * r + p * cr, ip * g + p * cg, ip * b + p * cb)
+        acc[0] += gr * (cr - r) + gg * (cg - g) + gb * (cb - b);
+        if (GIMG) {
+            const float ratio = cl * inv;
+            const float dratio = (0.5f * AISP_PIF * sn * den - cl) * inv * inv;
+            const float common = p * dratio * pass01(l0) * (gr * r + gg * g + gb * b);
+            const float k = ip + p * ratio;
+            gr = gr * k + common * 0.27f;
+            gg = gg * k + common * 0.67f;
+            gb = gb * k + common * 0.06f;
+        }
+    }
+};
+
+template <>
+struct PwBwd<AISP_OP_WNB> {
+    static constexpr int NACC = 1;
+    template <bool GIMG>
+    static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
+                                              float& gb, int clip, float* acc) {
+        const float p = c[0], ip = 1.f - p;
+        const float l = lum_isp(r, g, b);
+        AISP_MASK_CLIP(ip * r + p * l, ip * g + p * l, ip * b + p * l)
+        acc[0] += gr * (l - r) + gg * (l - g) + gb * (l - b);
+        if (GIMG) {
+            const float s = p * (gr + gg + gb);
+            gr = ip * gr + s * 0.27f;
+            gg = ip * gg + s * 0.67f;
+            gb = ip * gb + s * 0.06f;
+        }
+    }
+};
+
+template <>
+struct PwBwd<AISP_OP_SATPLUS> {
+    static constexpr int NACC = 1;
+    template <bool GIMG>
+    static __device__ __forceinline__ void px(const float* c, float r0, float g0, float b0, float& gr, float& gg,
+                                              float& gb, int clip, float* acc) {
+        const float p = c[0], ip = 1.f - p;
+        const float r = clip01(r0), g = clip01(g0), b = clip01(b0);
+        float fr, fg, fb;
+        HsvState st;
+        satplus_full(r, g, b, fr, fg, fb, st);
+        AISP_MASK_CLIP(r * ip + fr * p, g * ip + fg * p, b * ip + fb * p)
+        acc[0] += gr * (fr - r) + gg * (fg - g) + gb * (fb - b);
+        if (GIMG) {
+            // reverse sweep through hsv2rgb -> enhanced saturation -> rgb2hsv -> leading clip
+            float cr = gr * ip, cg = gg * ip, cb = gb * ip;
+            const float ar = gr * p, ag = gg * p, ab = gb * p;
+            float gv = 0.f, gp = 0.f, gq = 0.f, gt = 0.f;
+            switch (st.sextant) {
+            case 0: gv = ar; gt = ag; gp = ab; break;
+            case 1: gq = ar; gv = ag; gp = ab; break;
+            case 2: gp = ar; gv = ag; gt = ab; break;
+            case 3: gp = ar; gq = ag; gv = ab; break;
+            case 4: gt = ar; gp = ag; gv = ab; break;
+            case 5: gv = ar; gp = ag; gq = ab; break;
+            default: break;
+            }
+            const float s = st.s, f = st.f, vv = st.vv;
+            float gvv = gv + gp * (1.f - s) + gq * (1.f - f * s) + gt * (1.f - (1.f - f) * s);
+            const float gs = -vv * (gp + gq * f + gt * (1.f - f));
+            const float ghue6 = vv * s * (gt - gq);      // d/df; h*6 and hue/6 cancel, % has slope 1
+            const float gs2 = gs * pass01(st.s2);
+            float gmx = gvv * pass01(st.mx);
+            const float gsat = gs2 * (1.f - st.m * 0.8f);
+            const float gm = gs2 * (1.f - st.sat) * 0.8f;
+            const float sgn = (st.u > 0.f) ? 1.f : ((st.u < 0.f) ? -1.f : 0.f);  // abs'(0) = 0
+            gmx += gm * sgn;
+            float gmn = 0.f;
+            if (!st.satzero) {
+                const float den = st.mx + 1e-8f;
+                gmx += gsat * (1.0f / den - (st.mx - st.mn) / (den * den));
+                gmn -= gsat / den;
+            }
+            if (st.branch >= 0) {
+                const float gnum = ghue6 / st.d;
+                const float gd = -ghue6 * st.num / (st.d * st.d);
+                gmx += gd;
+                gmn -= gd;
+                if (st.branch == 0) { cg += gnum; cb -= gnum; }
+                else if (st.branch == 1) { cb += gnum; cr -= gnum; }
+                else { cr += gnum; cg -= gnum; }
+            }
+            // max / min route their gradient to the first arg-extremum in R,G,B order
+            if (r == st.mx) cr += gmx; else if (g == st.mx) cg += gmx; else cb += gmx;
+            if (r == st.mn) cr += gmn; else if (g == st.mn) cg += gmn; else cb += gmn;
+            gr = cr * pass01(r0);
+            gg = cg * pass01(g0);
+            gb = cb * pass01(b0);
+        }
+    }
+};
+
+// =============================================================================================
+// kernels
+// =============================================================================================
+__device__ __forceinline__ void stage_consts(const float* __restrict__ params, const int32_t* __restrict__ ops,
+                                             int b, int S, int len, float (*raw)[kConst], float (*sc)[kConst],
+                                             int* sop) {
+    // one warp per step loads the raw row, lane 0 derives the constants
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < len) {
+        raw[warp][lane] = (lane < AISP_PSTRIDE) ? params[((size_t)b * S + warp) * AISP_PSTRIDE + lane] : 0.f;
+        sc[warp][lane] = 0.f;
+        __syncwarp();
+        if (lane == 0) {
+            const int op = ops[(size_t)b * S + warp];
+            sop[warp] = op;
+            derive_consts(op, raw[warp], sc[warp]);
+        }
+    }
+    __syncthreads();
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads, 2)
+pw_fwd_kernel(const float* __restrict__ img, float* __restrict__ out, const float* __restrict__ params,
+              const int32_t* __restrict__ ops, const int32_t* __restrict__ seq_len, int N, int S, int clip_each) {
+    static_assert(AISP_MAX_STEPS <= kWarps, "one warp per step stages the constants");
+    __shared__ float raw[AISP_MAX_STEPS][kConst];
+    __shared__ float sc[AISP_MAX_STEPS][kConst];
+    __shared__ int sop[AISP_MAX_STEPS];
+    const int b = blockIdx.y;
+    int len = seq_len ? min(max(seq_len[b], 0), S) : S;
+    if (len > 0 && !is_pointwise(ops[(size_t)b * S])) {
+        // another family owns this sample -- except AISP_OP_NONE: the all-zero one-hot row of
+        // agent.py:18-23,154 (pdf_sample returned -1), whose gathered image is exactly zero
+        if (ops[(size_t)b * S] == AISP_OP_NONE) {
+            float* q = out + (size_t)b * 3 * (size_t)N;
+            const int c0 = blockIdx.x * kPwChunkPx;
+            for (int pl = 0; pl < 3; ++pl)
+                for (int i = c0 + threadIdx.x; i < min(c0 + kPwChunkPx, N); i += kThreads) q[(size_t)pl * N + i] = 0.f;
+        }
+        return;
+    }
+    stage_consts(params, ops, b, S, len, raw, sc, sop);
+    // a stencil op inside a sequence terminates it (documented in the header)
+    for (int k = 0; k < len; ++k)
+        if (!is_pointwise(sop[k])) { len = k; break; }
+
+    constexpr int GROUPS = kPwChunkPx / (kThreads * VEC);
+    constexpr int G = (VEC == 4) ? 4 : 8;  // groups handled together (16 or 8 px per thread per round)
+    constexpr int NPX = G * VEC;
+    const size_t base = (size_t)b * 3 * (size_t)N;
+    const float* pr = img + base;
+    float* qr = out + base;
+    const int chunk0 = blockIdx.x * kPwChunkPx;
+
+    for (int g0 = 0; g0 < GROUPS; g0 += G) {
+        float R[NPX], Gc[NPX], Bc[NPX];
+        Pack<VEC> t;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const int i = chunk0 + ((g0 + j) * kThreads + threadIdx.x) * VEC;
+            if (i < N) {
+                t.load(pr + i);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) R[j * VEC + v] = t.v[v];
+                t.load(pr + N + i);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) Gc[j * VEC + v] = t.v[v];
+                t.load(pr + 2 * (size_t)N + i);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) Bc[j * VEC + v] = t.v[v];
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { R[j * VEC + v] = 0.f; Gc[j * VEC + v] = 0.f; Bc[j * VEC + v] = 0.f; }
+            }
+        }
+        for (int k = 0; k < len; ++k) {
+            fwd_step<NPX>(sop[k], sc[k], R, Gc, Bc);
+            if (clip_each) {
+#pragma unroll
+                for (int i = 0; i < NPX; ++i) { R[i] = clip01(R[i]); Gc[i] = clip01(Gc[i]); Bc[i] = clip01(Bc[i]); }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const int i = chunk0 + ((g0 + j) * kThreads + threadIdx.x) * VEC;
+            if (i < N) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) t.v[v] = R[j * VEC + v];
+                t.store(qr + i);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) t.v[v] = Gc[j * VEC + v];
+                t.store(qr + N + i);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) t.v[v] = Bc[j * VEC + v];
+                t.store(qr + 2 * (size_t)N + i);
+            }
+        }
+    }
+}
+
+template <int OP, int VEC, bool GIMG>
+__device__ __forceinline__ void pw_bwd_body(const float* __restrict__ pr, const float* __restrict__ pg,
+                                            float* __restrict__ gi, const float* c, int N, int clip,
+                                            float* red, float* dst) {
+    constexpr int NACC = PwBwd<OP>::NACC;
+    constexpr int GROUPS = kPwChunkPx / (kThreads * VEC);
+    constexpr int G = (VEC == 4) ? 2 : 8;  // 8 px per thread per round: 12 LDG.128 in flight
+    float acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+    const int chunk0 = blockIdx.x * kPwChunkPx;
+    for (int g0 = 0; g0 < GROUPS; g0 += G) {
+        Pack<VEC> xr[G], xg[G], xb[G], dr[G], dg[G], db[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const int i = chunk0 + ((g0 + j) * kThreads + threadIdx.x) * VEC;
+            if (i < N) {
+                xr[j].load(pr + i); xg[j].load(pr + N + i); xb[j].load(pr + 2 * (size_t)N + i);
+                dr[j].load(pg + i); dg[j].load(pg + N + i); db[j].load(pg + 2 * (size_t)N + i);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    xr[j].v[v] = xg[j].v[v] = xb[j].v[v] = 0.f;
+                    dr[j].v[v] = dg[j].v[v] = db[j].v[v] = 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                PwBwd<OP>::template px<GIMG>(c, xr[j].v[v], xg[j].v[v], xb[j].v[v], dr[j].v[v], dg[j].v[v],
+                                             db[j].v[v], clip, acc);
+            if (GIMG) {
+                const int i = chunk0 + ((g0 + j) * kThreads + threadIdx.x) * VEC;
+                if (i < N) {
+                    dr[j].store(gi + i); dg[j].store(gi + N + i); db[j].store(gi + 2 * (size_t)N + i);
+                }
+            }
+        }
+    }
+    block_reduce_store<NACC>(acc, red, dst);
+}
+
+template <int VEC, bool GIMG>
+__global__ void __launch_bounds__(kThreads, 2)
+pw_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, const float* __restrict__ params,
+              const int32_t* __restrict__ ops, int N, int clip, float* __restrict__ gimg,
+              float* __restrict__ partial) {
+    __shared__ float raw[1][kConst];
+    __shared__ float sc[1][kConst];
+    __shared__ int sop[1];
+    __shared__ float red[kWarps * AISP_ACC_STRIDE];
+    const int b = blockIdx.y;
+    const int op = ops[b];
+    if (!is_pointwise(op)) {
+        if (GIMG && op == AISP_OP_NONE) {  // zero image -> zero gradient
+            float* q = gimg + (size_t)b * 3 * (size_t)N;
+            const int c0 = blockIdx.x * kPwChunkPx;
+            for (int pl = 0; pl < 3; ++pl)
+                for (int i = c0 + threadIdx.x; i < min(c0 + kPwChunkPx, N); i += kThreads) q[(size_t)pl * N + i] = 0.f;
+        }
+        return;
+    }
+    stage_consts(params, ops, b, 1, 1, raw, sc, sop);
+    const size_t base = (size_t)b * 3 * (size_t)N;
+    const float* pr = img + base;
+    const float* pg = gout + base;
+    float* gi = GIMG ? gimg + base : nullptr;
+    float* dst = partial + ((size_t)b * gridDim.x + blockIdx.x) * AISP_ACC_STRIDE;
+    const float* c = sc[0];
+    switch (op) {
+#define AISP_CASE(OPC) \
+    case OPC: pw_bwd_body<OPC, VEC, GIMG>(pr, pg, gi, c, N, clip, red, dst); break;
+        AISP_CASE(AISP_OP_EXPOSURE)
+        AISP_CASE(AISP_OP_GAMMA)
+        AISP_CASE(AISP_OP_WB)
+        AISP_CASE(AISP_OP_CCM)
+        AISP_CASE(AISP_OP_TONE)
+        AISP_CASE(AISP_OP_COLOR)
+        AISP_CASE(AISP_OP_CONTRAST)
+        AISP_CASE(AISP_OP_WNB)
+        AISP_CASE(AISP_OP_SATPLUS)
+#undef AISP_CASE
+    default: break;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+finalize_kernel(const float* __restrict__ partial, int nrows, const float* __restrict__ params,
+                const int32_t* __restrict__ ops, int family, float* __restrict__ grad_params) {
+    __shared__ double part[kWarps][AISP_ACC_STRIDE];
+    __shared__ double tot[AISP_ACC_STRIDE];
+    __shared__ float raw[kConst];
+    __shared__ float c[kConst];
+    const int b = blockIdx.x;
+    const int op = ops[b];
+    if (!in_family(op, family)) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* rows = partial + (size_t)b * nrows * AISP_ACC_STRIDE;
+    double s = 0.0;
+    for (int r = warp; r < nrows; r += kWarps) s += (double)rows[(size_t)r * AISP_ACC_STRIDE + lane];
+    part[warp][lane] = s;
+    if (warp == 0) {
+        raw[lane] = (lane < AISP_PSTRIDE) ? params[(size_t)b * AISP_PSTRIDE + lane] : 0.f;
+        c[lane] = 0.f;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += part[w][lane];
+        tot[lane] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        derive_consts(op, raw, c);
+        float gp[AISP_PSTRIDE];
+        finalize_grads(op, tot, c, raw, gp);
+        for (int k = 0; k < AISP_PSTRIDE; ++k) grad_params[(size_t)b * AISP_PSTRIDE + k] = gp[k];
+    }
+}
+
+// =============================================================================================
+// host-side launchers (called from capi.cu)
+// =============================================================================================
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+cudaError_t launch_pointwise_fwd(const float* img, float* out, const float* params, const int32_t* ops,
+                                 const int32_t* seq_len, int B, int H, int W, int S, int clip_each,
+                                 cudaStream_t st) {
+    const long long N = (long long)H * W;
+    dim3 grid((unsigned)((N + kPwChunkPx - 1) / kPwChunkPx), (unsigned)B);
+    const bool vec = (N % 4 == 0) && aligned16(img) && aligned16(out);
+    if (vec)
+        pw_fwd_kernel<4><<<grid, kThreads, 0, st>>>(img, out, params, ops, seq_len, (int)N, S, clip_each);
+    else
+        pw_fwd_kernel<1><<<grid, kThreads, 0, st>>>(img, out, params, ops, seq_len, (int)N, S, clip_each);
+    return cudaGetLastError();
+}
+
+int pointwise_rows(int H, int W) { return (int)(((long long)H * W + kPwChunkPx - 1) / kPwChunkPx); }
+
+cudaError_t launch_finalize(const float* partial, int nrows, const float* params, const int32_t* ops, int family,
+                            int B, float* grad_params, cudaStream_t st) {
+    finalize_kernel<<<B, kThreads, 0, st>>>(partial, nrows, params, ops, family, grad_params);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pointwise_bwd(const float* img, const float* gout, const float* params, const int32_t* ops,
+                                 int B, int H, int W, int clip, float* grad_params, float* grad_img,
+                                 float* partial, cudaStream_t st) {
+    const long long N = (long long)H * W;
+    const int rows = pointwise_rows(H, W);
+    dim3 grid((unsigned)rows, (unsigned)B);
+    const bool vec = (N % 4 == 0) && aligned16(img) && aligned16(gout) && (!grad_img || aligned16(grad_img));
+    if (vec) {
+        if (grad_img)
+            pw_bwd_kernel<4, true><<<grid, kThreads, 0, st>>>(img, gout, params, ops, (int)N, clip, grad_img, partial);
+        else
+            pw_bwd_kernel<4, false><<<grid, kThreads, 0, st>>>(img, gout, params, ops, (int)N, clip, nullptr, partial);
+    } else {
+        if (grad_img)
+            pw_bwd_kernel<1, true><<<grid, kThreads, 0, st>>>(img, gout, params, ops, (int)N, clip, grad_img, partial);
+        else
+            pw_bwd_kernel<1, false><<<grid, kThreads, 0, st>>>(img, gout, params, ops, (int)N, clip, nullptr, partial);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return launch_finalize(partial, rows, params, ops, FAMILY_POINTWISE, B, grad_params, st);
+}
+
+}  // namespace aisp

@@ -1,0 +1,334 @@
+// Halo-tiled 3x3 sharpen (two variants) and 5x5 unsharp mask for sm_100a, forward + backward.
+//
+//   SHARPEN     y = clip(x*f + blur3(x)*(1-f))      isp/sharpen.py:105-142  (1-px border keeps x)
+//   SHARPEN_V2  y = clip(x + (x - blur3(x))*f)      isp/sharpen.py:145-182
+//   USM         y = clip(x + (x - G_sigma*x)*a)     isp/sharpen.py:84-102   (5x5, reflect padding)
+//
+// CTA <-> (sample, 128x16 tile); the tile plus a 2-px halo of all three planes is staged in shared
+// memory once (border rule applied while staging), each thread produces a 4x2 block per plane from
+// registers (separable 5-tap passes for USM), so HBM sees ~24 B/px fwd and ~24 B/px bwd.
+#include "aisp_common.cuh"
+
+namespace aisp {
+
+constexpr int kHalo = 2;
+constexpr int kSmW = kShTileW + 8;             // 4 floats of left pad keep the interior 16B aligned
+constexpr int kSmH = kShTileH + 2 * kHalo;
+constexpr int kColOff = 4;                     // smem column of tile column 0
+
+__device__ __forceinline__ int reflect_clamp(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return min(max(i, 0), n - 1);
+}
+
+// stage tile + halo of one sample (3 planes) into shared memory
+__device__ __forceinline__ void stage_tile(const float* __restrict__ img, float (*sm)[kSmH][kSmW], int H, int W,
+                                           int x0, int y0) {
+    constexpr int CW = kShTileW + 2 * kHalo;  // 132 columns actually needed
+    for (int e = threadIdx.x; e < 3 * kSmH * CW; e += kThreads) {
+        const int ch = e / (kSmH * CW);
+        const int rem = e - ch * (kSmH * CW);
+        const int row = rem / CW, col = rem - row * CW;
+        const int gy = reflect_clamp(y0 - kHalo + row, H);
+        const int gx = reflect_clamp(x0 - kHalo + col, W);
+        sm[ch][row][col + kColOff - kHalo] = __ldg(img + ((size_t)ch * H + gy) * W + gx);
+    }
+}
+
+
+__device__ __forceinline__ void load_consts(const float* __restrict__ params, int b, int op, float* sc /*smem*/) {
+    if (threadIdx.x == 0) {
+        float raw[kConst];
+        for (int k = 0; k < AISP_PSTRIDE; ++k) raw[k] = params[(size_t)b * AISP_PSTRIDE + k];
+        for (int k = AISP_PSTRIDE; k < kConst; ++k) raw[k] = 0.f;
+        float c[kConst];
+        for (int k = 0; k < kConst; ++k) c[k] = 0.f;
+        derive_consts(op, raw, c);
+        for (int k = 0; k < kConst; ++k) sc[k] = c[k];
+    }
+}
+
+// blur (and optionally d blur / d sigma) of a 4x2 block for one plane.
+// (bx, by): block origin inside the tile.  blur[r][i], dblur[r][i].
+template <bool USM, bool WITH_D>
+__device__ __forceinline__ void block_blur(const float (*sm)[kSmW], int bx, int by, const float* sc, int gx0, int gy0,
+                                           int H, int W, float (&xc)[2][4], float (&blur)[2][4],
+                                           float (&dblur)[2][4]) {
+    if (USM) {
+        float hk[6][4], hd[6][4];
+        const float k0 = sc[0], k1 = sc[1], k2 = sc[2];
+        const float d0 = sc[5], d1 = sc[6], d2 = sc[7];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = sm[by + r][bx + kColOff - 2 + i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float e2 = v[i] + v[i + 4], e1 = v[i + 1] + v[i + 3], e0 = v[i + 2];
+                hk[r][i] = fmaf(k0, e2, fmaf(k1, e1, k2 * e0));
+                if (WITH_D) hd[r][i] = fmaf(d0, e2, fmaf(d1, e1, d2 * e0));
+                if (r >= 2 && r < 4) xc[r - 2][i] = e0;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float e2 = hk[r][i] + hk[r + 4][i], e1 = hk[r + 1][i] + hk[r + 3][i], e0 = hk[r + 2][i];
+                blur[r][i] = fmaf(k0, e2, fmaf(k1, e1, k2 * e0));
+                if (WITH_D) {
+                    const float f2 = hd[r][i] + hd[r + 4][i], f1 = hd[r + 1][i] + hd[r + 3][i], f0 = hd[r + 2][i];
+                    dblur[r][i] = fmaf(d0, e2, fmaf(d1, e1, d2 * e0)) + fmaf(k0, f2, fmaf(k1, f1, k2 * f0));
+                }
+            }
+    } else {
+        const float a = 1.0f / 13.0f, bc = 5.0f / 13.0f;
+        float hs[4][4], ctr[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float v[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) v[i] = sm[by + 1 + r][bx + kColOff - 1 + i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { hs[r][i] = (v[i] + v[i + 1]) + v[i + 2]; ctr[r][i] = v[i + 1]; }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float x = ctr[r + 1][i];
+                const float ring = (hs[r][i] + hs[r + 2][i]) + (hs[r + 1][i] - x);
+                const int gx = gx0 + i, gy = gy0 + r;
+                const bool border = (gx == 0) || (gy == 0) || (gx == W - 1) || (gy == H - 1);
+                xc[r][i] = x;
+                blur[r][i] = border ? x : fmaf(a, ring, bc * x);
+                if (WITH_D) dblur[r][i] = 0.f;
+            }
+    }
+}
+
+__device__ __forceinline__ float sharpen_value(int op, float x, float blur, float f) {
+    if (op == AISP_OP_SHARPEN) return x * f + blur * (1.0f - f);
+    return x + (x - blur) * f;  // SHARPEN_V2 and USM
+}
+
+template <bool BWD, bool WRITE_GY>
+__global__ void __launch_bounds__(kThreads, 2)
+sharpen_kernel(const float* __restrict__ img, const float* __restrict__ gout, float* __restrict__ out,
+               const float* __restrict__ params, const int32_t* __restrict__ ops, int H, int W, int vec,
+               float* __restrict__ partial) {
+    __shared__ __align__(16) float sm[3][kSmH][kSmW];
+    __shared__ float sc[kConst];
+    __shared__ float red[kWarps * AISP_ACC_STRIDE];
+    const int b = blockIdx.z;
+    const int op = ops[b];
+    if (!is_sharpen(op)) return;
+    const int x0 = blockIdx.x * kShTileW, y0 = blockIdx.y * kShTileH;
+    const size_t base = (size_t)b * 3 * H * W;
+    load_consts(params, b, op, sc);
+    stage_tile(img + base, sm, H, W, x0, y0);
+    __syncthreads();
+
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int bx = tx * 4, by = ty * 2;
+    const int gx0 = x0 + bx, gy0 = y0 + by;
+    const float f = (op == AISP_OP_USM) ? sc[10] : sc[0];
+    const bool vec_ok = vec && (gx0 + 3 < W);  // vec: W % 4 == 0 and 16B-aligned global pointers
+    float acc[2] = {0.f, 0.f};
+
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float xc[2][4], blur[2][4], dblur[2][4];
+        if (op == AISP_OP_USM)
+            block_blur<true, BWD>(sm[ch], bx, by, sc, gx0, gy0, H, W, xc, blur, dblur);
+        else
+            block_blur<false, BWD>(sm[ch], bx, by, sc, gx0, gy0, H, W, xc, blur, dblur);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int gy = gy0 + r;
+            if (gy >= H || gx0 >= W) continue;
+            const size_t off = base + ((size_t)ch * H + gy) * W + gx0;
+            float y[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[i] = sharpen_value(op, xc[r][i], blur[r][i], f);
+            if (!BWD) {
+                if (vec_ok) {
+                    stg_stream4(out + off, make_float4(clip01(y[0]), clip01(y[1]), clip01(y[2]), clip01(y[3])));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (gx0 + i < W) out[off + i] = clip01(y[i]);
+                }
+            } else {
+                float g[4];
+                if (vec_ok) {
+                    float4 t = ldg_stream4(gout + off);
+                    g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) g[i] = (gx0 + i < W) ? gout[off + i] : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    g[i] *= pass01(y[i]);
+                    if (gx0 + i < W) {
+                        if (op == AISP_OP_USM) {
+                            acc[0] = fmaf(g[i], dblur[r][i], acc[0]);
+                            acc[1] = fmaf(g[i], xc[r][i] - blur[r][i], acc[1]);
+                        } else {
+                            acc[0] = fmaf(g[i], xc[r][i] - blur[r][i], acc[0]);
+                        }
+                    }
+                }
+                if (WRITE_GY) {
+                    if (vec_ok) {
+                        stg_stream4(out + off, make_float4(g[0], g[1], g[2], g[3]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (gx0 + i < W) out[off + i] = g[i];
+                    }
+                }
+            }
+        }
+    }
+    if (BWD) {
+        const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+        const int ntiles = gridDim.x * gridDim.y;
+        block_reduce_store<2>(acc, red, partial + ((size_t)b * ntiles + tile) * AISP_ACC_STRIDE);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// transposed stencil: grad_img from the masked upstream gradient gy (staged by the kernel above)
+// CTA <-> (sample, 32x8 tile), one pixel per thread, all three planes.
+// ---------------------------------------------------------------------------------------------
+constexpr int kAdjW = 32, kAdjH = 8;
+
+__device__ __forceinline__ float gy_valid(const float* __restrict__ gy, int op, int H, int W, int y, int x) {
+    // gradient of output pixel (y,x) that flows through its blur term
+    if (y < 0 || y >= H || x < 0 || x >= W) return 0.f;
+    if (op != AISP_OP_USM && (y == 0 || x == 0 || y == H - 1 || x == W - 1)) return 0.f;  // border: blur == x
+    return gy[(size_t)y * W + x];
+}
+
+__device__ inline float gpad_at(const float* __restrict__ gy, int op, const float (*w)[5], int H, int W, int y,
+                                int x) {
+    // sum_k K(k) * gy(y - k): transposed correlation evaluated at a (possibly padded) position
+    float s = 0.f;
+    for (int dy = -2; dy <= 2; ++dy)
+        for (int dx = -2; dx <= 2; ++dx) s = fmaf(w[dy + 2][dx + 2], gy_valid(gy, op, H, W, y - dy, x - dx), s);
+    return s;
+}
+
+__device__ __forceinline__ int mirrors(int q, int n, int* m) {
+    // padded indices q' in [-2, n+1] whose reflect source is q (besides q itself)
+    int c = 0;
+    if (q >= 1 && q <= 2) m[c++] = -q;
+    const int hi = 2 * (n - 1) - q;
+    if (hi >= n && hi <= n + 1) m[c++] = hi;
+    return c;
+}
+
+__global__ void __launch_bounds__(kThreads)
+sharpen_adjoint_kernel(const float* __restrict__ gy, float* __restrict__ gimg, const float* __restrict__ params,
+                       const int32_t* __restrict__ ops, int H, int W) {
+    __shared__ float sm[3][kAdjH + 4][kAdjW + 4];
+    __shared__ float sc[kConst];
+    __shared__ float wk[5][5];
+    const int b = blockIdx.z;
+    const int op = ops[b];
+    if (!is_sharpen(op)) return;
+    const int x0 = blockIdx.x * kAdjW, y0 = blockIdx.y * kAdjH;
+    const size_t base = (size_t)b * 3 * H * W;
+    load_consts(params, b, op, sc);
+    __syncthreads();
+    if (threadIdx.x < 25) {
+        const int i = threadIdx.x / 5, j = threadIdx.x % 5;
+        float v;
+        if (op == AISP_OP_USM) v = sc[i] * sc[j];
+        else v = (i == 0 || i == 4 || j == 0 || j == 4) ? 0.f : ((i == 2 && j == 2) ? 5.0f / 13.0f : 1.0f / 13.0f);
+        wk[i][j] = v;
+    }
+    for (int e = threadIdx.x; e < 3 * (kAdjH + 4) * (kAdjW + 4); e += kThreads) {
+        const int ch = e / ((kAdjH + 4) * (kAdjW + 4));
+        const int rem = e - ch * ((kAdjH + 4) * (kAdjW + 4));
+        const int row = rem / (kAdjW + 4), col = rem - row * (kAdjW + 4);
+        sm[ch][row][col] = gy_valid(gy + base + (size_t)ch * H * W, op, H, W, y0 - 2 + row, x0 - 2 + col);
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int x = x0 + lx, y = y0 + ly;
+    if (x >= W || y >= H) return;
+    float alpha, beta;
+    if (op == AISP_OP_SHARPEN) { alpha = sc[0]; beta = 1.0f - sc[0]; }
+    else if (op == AISP_OP_SHARPEN_V2) { alpha = 1.0f + sc[0]; beta = -sc[0]; }
+    else { alpha = 1.0f + sc[10]; beta = -sc[10]; }
+    const bool border = (x == 0) || (y == 0) || (x == W - 1) || (y == H - 1);
+    int my[2], mx[2];
+    const int nmy = (op == AISP_OP_USM) ? mirrors(y, H, my) : 0;
+    const int nmx = (op == AISP_OP_USM) ? mirrors(x, W, mx) : 0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float* gch = gy + base + (size_t)ch * H * W;
+        float s = 0.f;
+#pragma unroll
+        for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+            for (int dx = -2; dx <= 2; ++dx) s = fmaf(wk[dy + 2][dx + 2], sm[ch][ly + 2 - dy][lx + 2 - dx], s);
+        // reflect padding folds the halo of the padded plane back onto its mirror pixels
+        for (int a = 0; a < nmy; ++a) s += gpad_at(gch, op, wk, H, W, my[a], x);
+        for (int c2 = 0; c2 < nmx; ++c2) s += gpad_at(gch, op, wk, H, W, y, mx[c2]);
+        for (int a = 0; a < nmy; ++a)
+            for (int c2 = 0; c2 < nmx; ++c2) s += gpad_at(gch, op, wk, H, W, my[a], mx[c2]);
+        const float g0 = gch[(size_t)y * W + x];
+        float v = alpha * g0 + beta * s;
+        if (op != AISP_OP_USM && border) v += beta * g0;
+        gimg[base + ((size_t)ch * H + y) * W + x] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------------
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int sharpen_rows(int H, int W) {
+    return ((W + kShTileW - 1) / kShTileW) * ((H + kShTileH - 1) / kShTileH);
+}
+
+cudaError_t launch_finalize(const float* partial, int nrows, const float* params, const int32_t* ops, int family,
+                            int B, float* grad_params, cudaStream_t st);
+
+cudaError_t launch_sharpen_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H,
+                               int W, cudaStream_t st) {
+    dim3 grid((W + kShTileW - 1) / kShTileW, (H + kShTileH - 1) / kShTileH, B);
+    const int vec = ((W & 3) == 0) && al16(out);
+    sharpen_kernel<false, false><<<grid, kThreads, 0, st>>>(img, nullptr, out, params, ops, H, W, vec, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sharpen_bwd(const float* img, const float* gout, const float* params, const int32_t* ops, int B,
+                               int H, int W, float* grad_params, float* grad_img, float* gy_scratch, float* partial,
+                               cudaStream_t st) {
+    dim3 grid((W + kShTileW - 1) / kShTileW, (H + kShTileH - 1) / kShTileH, B);
+    const int vec = ((W & 3) == 0) && al16(gout) && (!grad_img || al16(gy_scratch));
+    if (grad_img)
+        sharpen_kernel<true, true><<<grid, kThreads, 0, st>>>(img, gout, gy_scratch, params, ops, H, W, vec, partial);
+    else
+        sharpen_kernel<true, false><<<grid, kThreads, 0, st>>>(img, gout, nullptr, params, ops, H, W, vec, partial);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = launch_finalize(partial, sharpen_rows(H, W), params, ops, FAMILY_SHARPEN, B, grad_params, st);
+    if (e != cudaSuccess) return e;
+    if (grad_img) {
+        dim3 g2((W + kAdjW - 1) / kAdjW, (H + kAdjH - 1) / kAdjH, B);
+        sharpen_adjoint_kernel<<<g2, kThreads, 0, st>>>(gy_scratch, grad_img, params, ops, H, W);
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
+}  // namespace aisp

@@ -1,0 +1,242 @@
+"""Autograd-aware entry points over the C ABI (``include/aisp_b200.h``).
+
+``apply_ops`` is the one differentiable primitive: "apply op[b] with parameters P[b] to image b",
+for a homogeneous batch (one filter class, what ``Filter.process/forward`` needs) or a heterogeneous
+one (the policy-selected filter per sample, ``agent.py:103-116,154``).  ``chain_forward`` is the
+fused multi-step forward used for fixed chains and saved-pipeline replay.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import PSTRIDE, MAX_STEPS
+
+# op codes == enum aisp_op
+OP_EXPOSURE, OP_GAMMA, OP_CCM, OP_SHARPEN, OP_NLM, OP_TONE, OP_CONTRAST, OP_SATPLUS, OP_WNB, OP_WB, \
+    OP_USM, OP_COLOR, OP_SHARPEN_V2 = range(13)
+NUM_PARAMS = (1, 1, 9, 1, 1, 8, 1, 1, 1, 3, 2, 24, 1)
+POINTWISE = frozenset({OP_EXPOSURE, OP_GAMMA, OP_CCM, OP_TONE, OP_CONTRAST, OP_SATPLUS, OP_WNB, OP_WB, OP_COLOR})
+SHARPEN = frozenset({OP_SHARPEN, OP_SHARPEN_V2, OP_USM})
+
+FAMILY_POINTWISE, FAMILY_SHARPEN, FAMILY_NLM, FAMILY_MIXED = "pointwise", "sharpen", "nlm", "mixed"
+
+
+def family_of(op: int) -> str:
+    if op in POINTWISE:
+        return FAMILY_POINTWISE
+    if op in SHARPEN:
+        return FAMILY_SHARPEN
+    if op == OP_NLM:
+        return FAMILY_NLM
+    raise ValueError(f"unknown op {op}")
+
+
+def pack_params(param: torch.Tensor, n: int) -> torch.Tensor:
+    """Reference-layout parameter tensor (e.g. Tone ``[B,8,1,1,1]``) -> packed ``[B,PSTRIDE]`` row."""
+    flat = param.reshape(param.shape[0], n)
+    if flat.dtype != torch.float32:
+        raise _lib.AispError(f"filter parameters must be float32, got {flat.dtype}")
+    return torch.nn.functional.pad(flat, (0, PSTRIDE - n))
+
+
+def _ops_tensor(ops, B: int, device) -> torch.Tensor:
+    if isinstance(ops, int):
+        return torch.full((B,), ops, dtype=torch.int32, device=device)
+    if ops.dtype != torch.int32:
+        ops = ops.to(torch.int32)
+    if not ops.is_cuda:
+        raise _lib.AispError("ops must live on the GPU (no host round trip on the hot path)")
+    return ops.contiguous()
+
+
+class _ApplyOps(torch.autograd.Function):
+    """out[b] = [clip](process_{ops[b]}(img[b], P[b]))  with analytic backward in CUDA."""
+
+    @staticmethod
+    def forward(ctx, img, P, ops, clip: bool, family: str):
+        _lib.require_image(img, "img")
+        B, _, H, W = img.shape
+        if P.shape != (B, PSTRIDE) or not P.is_cuda or P.dtype != torch.float32:
+            raise _lib.AispError(f"packed params must be CUDA float32 [B,{PSTRIDE}], got {tuple(P.shape)} {P.dtype}")
+        P = P.contiguous()
+        L = _lib.lib()
+        st = _lib.stream_ptr(img.device)
+        out = torch.empty_like(img)
+        want_pgrad = ctx.needs_input_grad[1]
+        stash = None
+        if family in (FAMILY_NLM, FAMILY_MIXED) and want_pgrad:
+            stash = torch.empty_like(img)
+        with torch.cuda.device(img.device):
+            if family == FAMILY_POINTWISE:
+                rc = L.aisp_pointwise_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), ops.data_ptr(), None,
+                                          B, H, W, 1, int(clip), st)
+            elif family == FAMILY_SHARPEN:
+                rc = L.aisp_sharpen_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), ops.data_ptr(), B, H, W, st)
+            elif family == FAMILY_NLM:
+                rc = L.aisp_nlm_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), ops.data_ptr(), B, H, W,
+                                    _lib.ptr(stash), st)
+            else:
+                rc = L.aisp_select_apply_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), ops.data_ptr(),
+                                             B, H, W, int(clip), _lib.ptr(stash), st)
+        _lib.check(rc, f"aisp {family} forward")
+        ctx.save_for_backward(img, P, ops, stash)
+        ctx.clip = bool(clip)
+        ctx.family = family
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        img, P, ops, stash = ctx.saved_tensors
+        B, _, H, W = img.shape
+        need_img, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_img or need_p):
+            return None, None, None, None, None
+        g = g.contiguous()
+        if g.dtype != torch.float32:
+            raise _lib.AispError("grad_out must be float32")
+        L = _lib.lib()
+        st = _lib.stream_ptr(img.device)
+        family = ctx.family
+        gP = torch.zeros_like(P)
+        gimg = torch.empty_like(img) if need_img else None
+        gy = None
+        if need_img and family in (FAMILY_SHARPEN, FAMILY_MIXED):
+            gy = torch.empty_like(img)
+        if need_img and family in (FAMILY_NLM, FAMILY_MIXED) and (
+                family == FAMILY_NLM or bool((ops == OP_NLM).any())):
+            raise NotImplementedError(
+                "d/d img of the NLM denoise filter is not implemented (the reference's training never asks for it: "
+                "train.py:255 makes the image a leaf); detach the image or exclude NLM samples")
+        sc = _lib.scratch(B, H, W, img.device)
+        with torch.cuda.device(img.device):
+            if family == FAMILY_POINTWISE:
+                rc = L.aisp_pointwise_bwd(img.data_ptr(), g.data_ptr(), P.data_ptr(), ops.data_ptr(), B, H, W,
+                                          int(ctx.clip), gP.data_ptr(), _lib.ptr(gimg), sc.data_ptr(), sc.numel(), st)
+            elif family == FAMILY_SHARPEN:
+                rc = L.aisp_sharpen_bwd(img.data_ptr(), g.data_ptr(), P.data_ptr(), ops.data_ptr(), B, H, W,
+                                        gP.data_ptr(), _lib.ptr(gimg), _lib.ptr(gy), sc.data_ptr(), sc.numel(), st)
+            elif family == FAMILY_NLM:
+                if stash is None:
+                    raise _lib.AispError("NLM backward needs the d out/d h stash written by the forward")
+                rc = L.aisp_nlm_bwd(g.data_ptr(), stash.data_ptr(), ops.data_ptr(), B, H, W, gP.data_ptr(), None,
+                                    sc.data_ptr(), sc.numel(), st)
+            else:
+                rc = L.aisp_select_apply_bwd(img.data_ptr(), g.data_ptr(), P.data_ptr(), ops.data_ptr(), B, H, W,
+                                             int(ctx.clip), None if need_img else _lib.ptr(stash), gP.data_ptr(),
+                                             _lib.ptr(gimg), _lib.ptr(gy), sc.data_ptr(), sc.numel(), st)
+        _lib.check(rc, f"aisp {family} backward")
+        return gimg, (gP if need_p else None), None, None, None
+
+
+def apply_ops(img: torch.Tensor, P: torch.Tensor, ops, clip: bool, family: Optional[str] = None) -> torch.Tensor:
+    """Apply ``ops[b]`` (int or int32 CUDA tensor ``[B]``) with packed parameters ``P[b]``.
+
+    ``clip=True`` reproduces ``Filter.forward`` (isp/filters.py:115,125), ``clip=False``
+    ``Filter.process`` / ``run`` (:138).  ``family`` narrows the launch to one kernel family when the
+    caller knows the batch is homogeneous; ``None`` means heterogeneous ("mixed": three launches).
+    """
+    if isinstance(ops, int) and family is None:
+        family = family_of(ops)
+    ops_t = _ops_tensor(ops, img.shape[0], img.device)
+    return _ApplyOps.apply(img, P, ops_t, clip, family or FAMILY_MIXED)
+
+
+def apply_filter(img: torch.Tensor, param: torch.Tensor, op: int, clip: bool) -> torch.Tensor:
+    """One filter class on the whole batch; ``param`` in the reference's own layout."""
+    return apply_ops(img, pack_params(param, NUM_PARAMS[op]), op, clip, family_of(op))
+
+
+@torch.no_grad()
+def chain_forward(img: torch.Tensor, P: torch.Tensor, ops: torch.Tensor, seq_len: Optional[torch.Tensor] = None,
+                  clip_each: bool = True) -> torch.Tensor:
+    """Per-sample sequences of per-pixel filters fused into ONE pass over HBM (forward only).
+
+    img ``[B,3,H,W]``; P ``[B,S,PSTRIDE]``; ops int32 ``[B,S]``; seq_len int32 ``[B]`` or None.
+    Stencil ops are not allowed inside a fused sequence (use ``run_pipeline`` for mixed sequences).
+    """
+    _lib.require_image(img, "img")
+    B, _, H, W = img.shape
+    S = ops.shape[1]
+    if not (1 <= S <= MAX_STEPS):
+        raise _lib.AispError(f"sequence length {S} outside 1..{MAX_STEPS}")
+    if P.shape != (B, S, PSTRIDE) or P.dtype != torch.float32 or not P.is_cuda:
+        raise _lib.AispError(f"P must be CUDA float32 [B,S,{PSTRIDE}]")
+    ops = _ops_tensor(ops, B, img.device)
+    if seq_len is not None:
+        seq_len = _ops_tensor(seq_len, B, img.device)
+    out = torch.empty_like(img)
+    with torch.cuda.device(img.device):
+        rc = _lib.lib().aisp_pointwise_fwd(img.data_ptr(), out.data_ptr(), P.contiguous().data_ptr(), ops.data_ptr(),
+                                           _lib.ptr(seq_len), B, H, W, S, int(clip_each), _lib.stream_ptr(img.device))
+    _lib.check(rc, "aisp_pointwise_fwd")
+    return out
+
+
+@torch.no_grad()
+def run_pipeline(img: torch.Tensor, steps: Sequence[Sequence[int]], params: Sequence[Sequence[torch.Tensor]],
+                 clip_each: bool = True) -> torch.Tensor:
+    """Replay known per-sample pipelines (``param_results/*.json`` of yolov3/val_adaptiveisp.py:301-327).
+
+    ``steps[b]`` is the list of op codes of sample b, ``params[b][k]`` the flat parameter tensor of its
+    k-th step.  Consecutive per-pixel steps are fused into one pass; a stencil step forces a pass
+    boundary.  Samples are advanced phase by phase: phase p runs every sample's p-th fused segment in
+    one heterogeneous launch (samples that already finished are carried through unchanged).
+    """
+    _lib.require_image(img, "img")
+    B = img.shape[0]
+    dev = img.device
+    # split each sample's sequence into segments: runs of per-pixel ops, or a single stencil op
+    segs = []
+    for b in range(B):
+        cur, out = [], []
+        for k, op in enumerate(steps[b]):
+            if op in POINTWISE:
+                cur.append(k)
+                if len(cur) == MAX_STEPS:
+                    out.append(cur)
+                    cur = []
+            else:
+                if cur:
+                    out.append(cur)
+                    cur = []
+                out.append([k])
+        if cur:
+            out.append(cur)
+        segs.append(out)
+    nphase = max((len(s) for s in segs), default=0)
+    x = img
+    for p in range(nphase):
+        S = max(len(s[p]) if p < len(s) else 0 for s in segs)
+        ops_h = torch.zeros((B, S), dtype=torch.int32)
+        len_h = torch.zeros((B,), dtype=torch.int32)
+        P_h = torch.zeros((B, S, PSTRIDE), dtype=torch.float32)
+        for b in range(B):
+            if p >= len(segs[b]):
+                continue  # seq_len 0 == identity for the per-pixel kernel
+            for j, k in enumerate(segs[b][p]):
+                op = steps[b][k]
+                ops_h[b, j] = op
+                P_h[b, j, :NUM_PARAMS[op]] = params[b][k].detach().reshape(-1).float().cpu()
+            len_h[b] = len(segs[b][p])
+        ops_d, len_d, P_d = ops_h.to(dev), len_h.to(dev), P_h.to(dev)
+        nxt = chain_forward(x, P_d, ops_d, len_d, clip_each)      # skips samples led by a stencil op
+        first = ops_h[:, 0]
+        active = len_h > 0
+        if bool((active & torch.isin(first, torch.tensor(sorted(SHARPEN), dtype=torch.int32))).any()) or \
+                bool((active & (first == OP_NLM)).any()):
+            # stencil segments have length 1: run the two stencil families on the same buffers;
+            # inactive samples carry op -1 there (skipped) and were copied through by chain_forward
+            st_ops = torch.where(active, first, torch.full_like(first, -1)).to(dev)
+            L = _lib.lib()
+            Bn, _, H, W = x.shape
+            P1 = P_d[:, 0, :].contiguous()
+            with torch.cuda.device(dev):
+                _lib.check(L.aisp_sharpen_fwd(x.data_ptr(), nxt.data_ptr(), P1.data_ptr(), st_ops.data_ptr(), Bn, H, W,
+                                              _lib.stream_ptr(dev)), "aisp_sharpen_fwd")
+                _lib.check(L.aisp_nlm_fwd(x.data_ptr(), nxt.data_ptr(), P1.data_ptr(), st_ops.data_ptr(), Bn, H, W,
+                                          None, _lib.stream_ptr(dev)), "aisp_nlm_fwd")
+        x = nxt
+    return x if nphase > 0 else img.clone()

@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native ISP filter chain (BASELINE.json metric: ISP-chain megapixels/s,
+forward + backward, and the fraction of the HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): the full filter set of cfg.filters (E, G, CCM, Shr, NLM, T, Ct,
+S+, BW, W -- config.py:19-22), each applied forward (Filter.forward semantics, clip fused) and
+backward (parameter gradients: the training case, train.py:255) to a batch of 64 synthetic
+LOD-shaped 512x512 frames per GPU.  One "step" = those 10 filter applications fwd+bwd; megapixels
+per step = 10 * B * H * W / 1e6.  This is what the reference's Agent.forward + backward does to the
+ISP filters in one training iteration (agent.py:103-109 runs all ten on the whole batch).
+
+  value  : resident inputs, straight through the C ABI (ctypes -> libaisp_b200.so)
+  e2e    : through the drop-in Filter classes (FC layers + regressors + autograd + kernels) with
+           the image batch coming from pinned HOST memory every step and one output batch going
+           back to the host every step (train.py:255 / :378-381)
+  roofline / kernels : per-kernel CUDA-event timing inside the timed region
+  cpu_baseline : the CPU oracle port of the reference's PyTorch path on the host cores (bounded sample)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU, H, W = 64, 512, 512
+WORKLOAD = "configs[1]: full filter set (10 cfg.filters) fwd+bwd, batch=64 x 512x512 per GPU, synthetic LOD-shaped"
+METRIC = "isp_chain_megapixels_per_sec_fwd_bwd"
+ALGO_BYTES_FWD, ALGO_BYTES_BWD = 24, 24  # B/px, SURVEY.md §8(d): fwd r12+w12, bwd (param grads) r12+r12
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi in the background, samples kept only inside the timed region)
+# ----------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def summary(self, windows):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.samples:
+            if not any(a <= t <= b for a, b in windows):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's PyTorch path (bench.py's only use of oracle/)
+# ----------------------------------------------------------------------------------------------
+def cpu_step(sample_b, reps):
+    """10 filters fwd+bwd on `sample_b` frames through the CPU oracle; returns (MP/s, seconds, cores)."""
+    from oracle import isp_oracle as O
+    from adaptiveisp_b200.synthetic import lod_batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    img = lod_batch(sample_b, H, W, seed=1235)
+    g = torch.randn(img.shape, generator=torch.Generator().manual_seed(1))
+    ops = list(range(10))
+    feats = {op: torch.randn((sample_b, O.OP_NPARAMS[op]), generator=torch.Generator().manual_seed(op)) * 0.5
+             for op in ops}
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        for op in ops:
+            f = feats[op].clone().requires_grad_(True)
+            y = O.forward(op, img, O.regress(op, f))
+            y.backward(g)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return 10 * sample_b * H * W / 1e6 / best, best, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_b = 1
+    times = []
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_step(sample_b, 1)
+    steps = max(1, min(args.steps, 3))
+    for _ in range(steps):
+        mps, dt, cores = cpu_step(sample_b, 1)
+        times.append(dt)
+    dt = sum(times) / len(times)
+    value = 10 * sample_b * H * W / 1e6 / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU PyTorch path of the reference (oracle port, same ATen ops), "
+                                                 f"each step a bounded sample of {sample_b} frame(s) of the batch"},
+        "cpu_baseline": {"value": value, "unit": "MP/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample_b} of 64 frames, 10 filters fwd+bwd, {steps} step(s) averaged"},
+        "e2e": {"value": value, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from adaptiveisp_b200 import _lib, functional as AF
+    from adaptiveisp_b200 import filters as Fm
+    from adaptiveisp_b200.config import make_cfg
+    from adaptiveisp_b200.synthetic import lod_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the ISP kernels have no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    clocks = Clocks(local) if rank == 0 else None
+
+    B = B_PER_GPU
+    cfg = make_cfg()
+    img = lod_batch(B, H, W, seed=1235 + rank, device=dev)
+    gout = torch.randn(img.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+    out = torch.empty_like(img)
+    stash = torch.empty_like(img)
+    flts = [c(cfg, predict=True).to(dev) for c in cfg.filters]
+    gen = torch.Generator().manual_seed(99)
+    feats = torch.randn((B, cfg.feature_extractor_dims), generator=gen).to(dev)
+    # resident packed parameters per filter, produced once by the filters' own regressors
+    with torch.no_grad():
+        packed = []
+        for f in flts:
+            raw, _ = f.extract_parameters(feats * 0.05)
+            packed.append(AF.pack_params(f.filter_param_regressor(raw), f.get_num_filter_parameters()).contiguous())
+    ops_t = [torch.full((B,), f.OP, dtype=torch.int32, device=dev) for f in flts]
+    gP = torch.zeros((B, 24), device=dev)
+    scratch = _lib.scratch(B, H, W, dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    names = [f.get_short_name() for f in flts]
+
+    def fwd(i):
+        f, P, o = flts[i], packed[i], ops_t[i]
+        fam = AF.family_of(f.OP)
+        if fam == AF.FAMILY_POINTWISE:
+            rc = L.aisp_pointwise_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), o.data_ptr(), None, B, H, W, 1, 1, st)
+        elif fam == AF.FAMILY_SHARPEN:
+            rc = L.aisp_sharpen_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), o.data_ptr(), B, H, W, st)
+        else:
+            rc = L.aisp_nlm_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), o.data_ptr(), B, H, W, stash.data_ptr(), st)
+        _lib.check(rc, "fwd " + names[i])
+
+    def bwd(i):
+        f, P, o = flts[i], packed[i], ops_t[i]
+        fam = AF.family_of(f.OP)
+        if fam == AF.FAMILY_POINTWISE:
+            rc = L.aisp_pointwise_bwd(img.data_ptr(), gout.data_ptr(), P.data_ptr(), o.data_ptr(), B, H, W, 1,
+                                      gP.data_ptr(), None, scratch.data_ptr(), scratch.numel(), st)
+        elif fam == AF.FAMILY_SHARPEN:
+            rc = L.aisp_sharpen_bwd(img.data_ptr(), gout.data_ptr(), P.data_ptr(), o.data_ptr(), B, H, W,
+                                    gP.data_ptr(), None, None, scratch.data_ptr(), scratch.numel(), st)
+        else:
+            rc = L.aisp_nlm_bwd(gout.data_ptr(), stash.data_ptr(), o.data_ptr(), B, H, W, gP.data_ptr(), None,
+                                scratch.data_ptr(), scratch.numel(), st)
+        _lib.check(rc, "bwd " + names[i])
+
+    nf = len(flts)
+    launches_per_step = nf * 3  # fwd kernel + bwd kernel + finalize kernel per filter
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    # ---------------- value: resident inputs, C ABI ----------------
+    for _ in range(max(args.warmup, 3)):
+        for i in range(nf):
+            fwd(i)
+            bwd(i)
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+            torch.cuda.Event(enable_timing=True)) for _ in range(nf)] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    tw0 = time.time()
+    e0.record()
+    for s in range(args.steps):
+        for i in range(nf):
+            a, b_, c = ev[s][i]
+            a.record()
+            fwd(i)
+            b_.record()
+            bwd(i)
+            c.record()
+    e1.record()
+    barrier()
+    tw1 = time.time()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    px_step = nf * B * H * W
+    value = world * px_step * args.steps / 1e6 / (ms_max / 1e3)
+
+    # per-kernel durations from the events recorded inside the timed region
+    kern = {}
+    for i in range(nf):
+        tf = sum(ev[s][i][0].elapsed_time(ev[s][i][1]) for s in range(args.steps)) / args.steps
+        tb = sum(ev[s][i][1].elapsed_time(ev[s][i][2]) for s in range(args.steps)) / args.steps
+        kern[names[i]] = (tf, tb)
+
+    # ---------------- e2e: host buffers, public class API ----------------
+    host_img = torch.empty(img.shape, dtype=torch.float32, pin_memory=True)
+    host_img.copy_(img.cpu())
+    host_out = torch.empty(img.shape, dtype=torch.float32, pin_memory=True)
+    host_feat = torch.empty(feats.shape, dtype=torch.float32, pin_memory=True)
+    host_feat.copy_((feats * 0.05).cpu())
+    for f in flts:
+        f.train()
+
+    def e2e_step():
+        x = host_img.to(dev, non_blocking=True)
+        ft = host_feat.to(dev, non_blocking=True)
+        last = None
+        for f in flts:
+            y, _, _ = f(x, ft)
+            y.backward(gout)
+            last = y
+        host_out.copy_(last.detach(), non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    tw2 = time.time()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    tw3 = time.time()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * px_step * e2e_steps / 1e6 / (float(t.item()) / 1e3)
+    h2d = host_img.numel() * 4 + host_feat.numel() * 4
+    d2h = host_out.numel() * 4
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        npx = B * H * W
+        klist = []
+        for n, (tf, tb) in kern.items():
+            klist.append({"filter": n, "fwd_ms": round(tf, 4), "bwd_ms": round(tb, 4),
+                          "fwd_GBs": round(ALGO_BYTES_FWD * npx / 1e9 / (tf / 1e3), 1),
+                          "bwd_GBs": round(ALGO_BYTES_BWD * npx / 1e9 / (tb / 1e3), 1)})
+        # dominant kernel of the step by time
+        dom = max(klist, key=lambda k: max(k["fwd_ms"], k["bwd_ms"]))
+        dom_fwd = dom["fwd_ms"] >= dom["bwd_ms"]
+        ach = dom["fwd_GBs"] if dom_fwd else dom["bwd_GBs"]
+        pw = [k for k in klist if k["filter"] not in ("NLM",)]
+        pw_bytes = sum((ALGO_BYTES_FWD + ALGO_BYTES_BWD) * npx for _ in pw)
+        pw_ms = sum(k["fwd_ms"] + k["bwd_ms"] for k in pw)
+        step_bytes = (ALGO_BYTES_FWD + ALGO_BYTES_BWD) * npx * nf
+        line = {
+            "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "height": H, "width": W, "filters": names,
+                       "l2": "inputs (201 MB image + 201 MB upstream gradient per GPU) exceed the 126 MB L2; no flush",
+                       "parallelism": f"dp{world} (batch-sharded replicas, no collective in the ISP path)"},
+            "roofline": {"bound": "hbm", "kernel": ("nlm_kernel<grad>" if dom["filter"] == "NLM" else dom["filter"]) +
+                         (" fwd" if dom_fwd else " bwd"), "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "NLM is FP32/MUFU-bound by construction (121 patch distances, sqrt and exp per "
+                                 "pixel), see DESIGN.md; HBM fractions of the HBM-bound kernels are in 'kernels'"},
+            "hbm_frac_step": step_bytes / 1e9 / (ms_max / args.steps / 1e3) / peak,
+            "hbm_frac_excl_nlm": pw_bytes / 1e9 / (pw_ms / 1e3) / peak,
+            "kernels": klist,
+            "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks.summary([(tw0, tw1), (tw2, tw3)]),
+        }
+        if world == 1 and not args.no_cpu:
+            mps, dt, cores = cpu_step(1, 2)
+            line["cpu_baseline"] = {"value": mps, "unit": "MP/s", "cores": cores, "kind": "port",
+                                    "sample": "1 of 64 frames, same 10 filters fwd+bwd, best of 2 (%.2f s each)" % dt}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,166 @@
+/*
+ * aisp_b200.h -- C ABI of the B200-native (sm_100a) differentiable ISP filter chain.
+ *
+ * This is the drop-in boundary for the hot path of OpenImagingLab/AdaptiveISP: the arithmetic
+ * behind `Filter.process` / `Filter.forward` / `Filter.run` of isp/filters.py (with isp/denoise.py
+ * and isp/sharpen.py) and the "apply the selected filter" step of agent.py:103-116,154.  The
+ * reference has no FFI of its own (it is pure PyTorch); each entry point below cites the reference
+ * code it replaces, and INTEGRATION.md shows the Python (ctypes) stub a maintainer binds it with.
+ *
+ * Conventions
+ *   - all image tensors are device pointers to fp32, NCHW, contiguous, C == 3: [B,3,H,W];
+ *   - `params` is a packed row per (sample, step): AISP_PSTRIDE floats, holding the filter's
+ *     parameters exactly as the reference's `filter_param_regressor` returns them, flattened
+ *     (Tone [B,8,1,1,1] -> 8 floats; Color [B,8,3,1,1] -> 24 floats knot-major; CCM 9 floats
+ *     row-major; USM (sigma, amount); everything else 1 or 3 floats); unused tail is ignored;
+ *   - `ops` holds one enum aisp_op per (sample, step): the policy-selected filter;
+ *   - every buffer is caller-owned and only borrowed for the call; no hidden allocation, scratch
+ *     is passed in; all work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = the
+ *     legacy default stream) of the current device; functions are stateless and re-entrant;
+ *   - return value: 0 on success, a negative aisp_status for argument errors, or a positive
+ *     cudaError_t from the launch.  There is no CPU fallback anywhere.
+ */
+#ifndef AISP_B200_H
+#define AISP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Filter op codes.  0..9 follow the order of cfg.filters (config.py:19-22). */
+enum aisp_op {
+    AISP_OP_NONE       = -1, /* no filter selected (all-zero one-hot row, agent.py:18-23,154):
+                                the output image is exactly 0 and all gradients are 0            */
+    AISP_OP_EXPOSURE   = 0,  /* ExposureFilter              isp/filters.py:215-224   1 param  */
+    AISP_OP_GAMMA      = 1,  /* GammaFilter                 isp/filters.py:235-245   1        */
+    AISP_OP_CCM        = 2,  /* CCMFilter                   isp/filters.py:694-708   9        */
+    AISP_OP_SHARPEN    = 3,  /* SharpenFilter (3x3)         isp/filters.py:621-631   1        */
+    AISP_OP_NLM        = 4,  /* DenoiseFilter (NLM gray)    isp/filters.py:571-586   1        */
+    AISP_OP_TONE       = 5,  /* ToneFilter                  isp/filters.py:326-347   8        */
+    AISP_OP_CONTRAST   = 6,  /* ContrastFilter              isp/filters.py:406-419   1        */
+    AISP_OP_SATPLUS    = 7,  /* SaturationPlusFilter        isp/filters.py:536-560   1        */
+    AISP_OP_WNB        = 8,  /* WNBFilter (desaturation)    isp/filters.py:427-437   1        */
+    AISP_OP_WB         = 9,  /* ImprovedWhiteBalanceFilter  isp/filters.py:253-272   3        */
+    AISP_OP_USM        = 10, /* SharpenUSMFilter (5x5)      isp/filters.py:597-608   2        */
+    AISP_OP_COLOR      = 11, /* ColorFilter                 isp/filters.py:281-303   24       */
+    AISP_OP_SHARPEN_V2 = 12, /* SharpenFilterV2             isp/filters.py:644-653   1        */
+    AISP_OP_COUNT      = 13
+};
+
+#define AISP_PSTRIDE   24 /* floats per (sample, step) parameter row */
+#define AISP_MAX_STEPS 8  /* longest fused per-sample sequence        */
+#define AISP_ACC_STRIDE 32 /* floats per partial-sum row in the backward scratch */
+
+enum aisp_status {
+    AISP_OK              = 0,
+    AISP_ERR_NULL        = -1, /* a required pointer is NULL                          */
+    AISP_ERR_SHAPE       = -2, /* B/H/W/S out of range                                */
+    AISP_ERR_SCRATCH     = -3, /* scratch buffer too small                            */
+    AISP_ERR_UNSUPPORTED = -4, /* combination not implemented (never silently wrong)  */
+    AISP_ERR_ALIGN       = -5  /* pointer not 4-byte aligned                          */
+};
+
+/* Library ABI version (bumped on any signature change) and status text. */
+int         aisp_version(void);
+const char* aisp_status_string(int status);
+
+/* Number of parameters of an op (aisp_op), or -1. */
+int aisp_op_num_params(int op);
+
+/*
+ * Fused per-pixel pass, forward.  Replaces, for the per-pixel filters
+ * (E, G, CCM, T, Ct, S+, BW, W, C), `lerp(img, process(img,p), 1)` [+ clip] of
+ * isp/filters.py:115,125 / :138, applied `seq_len[b]` times in ONE pass over HBM with the
+ * per-sample op sequence ops[b, 0..seq_len[b]) -- the heterogeneous "policy-selected filter
+ * sequence" of agent.py:103-154 / yolov3/val_adaptiveisp.py:291-309 replay.
+ *   img, out   [B,3,H,W]; out must not alias img
+ *   params     [B,S,AISP_PSTRIDE]     ops [B,S] int32     seq_len [B] int32 or NULL (= S everywhere)
+ *   clip_each  1: clip to [0,1] after every step (Filter.forward semantics)
+ *              0: never clip (Filter.run semantics, isp/filters.py:128-139)
+ * Samples whose FIRST op is a stencil op (SHARPEN, SHARPEN_V2, USM, NLM) are skipped entirely
+ * (their `out` rows are left untouched) so that the three family entry points can be issued
+ * back to back on a heterogeneous batch; a stencil op later in a sequence ends the sequence there.
+ */
+int aisp_pointwise_fwd(const float* img, float* out, const float* params, const int32_t* ops,
+                       const int32_t* seq_len, int B, int H, int W, int S, int clip_each, void* stream);
+
+/* Scratch bytes required by any *_bwd entry point for a [B,3,H,W] batch. */
+size_t aisp_bwd_scratch_bytes(int B, int H, int W);
+
+/*
+ * Fused per-pixel pass, backward of ONE step per sample (what autograd does for
+ * isp/filters.py:115,125 when train.py:341-342 calls backward()): the forward value is
+ * recomputed in registers from `img`; parameter gradients are reduced warp-shuffle -> block ->
+ * per-sample (fixed order, fp64 final combine: deterministic run to run).
+ *   grad_out    [B,3,H,W]  upstream dL/dout
+ *   clip        1 if the forward was Filter.forward (clip backward: pass iff 0 <= y <= 1)
+ *   grad_params [B,AISP_PSTRIDE]   written (all PSTRIDE entries) for every non-skipped sample
+ *   grad_img    [B,3,H,W] or NULL (NULL in training: train.py:255 makes img a leaf without grad)
+ *   scratch     >= aisp_bwd_scratch_bytes(B,H,W) bytes of device memory
+ * Samples whose op is a stencil op are skipped (see aisp_pointwise_fwd).
+ */
+int aisp_pointwise_bwd(const float* img, const float* grad_out, const float* params, const int32_t* ops,
+                       int B, int H, int W, int clip, float* grad_params, float* grad_img,
+                       void* scratch, size_t scratch_bytes, void* stream);
+
+/*
+ * 3x3 sharpen (SHARPEN: adjust_sharpness isp/sharpen.py:105-142; SHARPEN_V2: sharpness :145-182)
+ * and 5x5 unsharp mask (USM: unsharp_mask isp/sharpen.py:84-102 with reflect padding, per-sample
+ * sigma/amount -- the reference loops over the batch in Python, :91-96).  Halo-tiled in shared
+ * memory.  All three clip to [0,1] internally, so there is no clip flag.
+ * Samples whose op is not one of the three are skipped.
+ */
+int aisp_sharpen_fwd(const float* img, float* out, const float* params, const int32_t* ops,
+                     int B, int H, int W, void* stream);
+
+/*
+ * Backward of the above.  grad_params: SHARPEN/SHARPEN_V2 -> [0] = d/dfactor;
+ * USM -> [0] = d/dsigma, [1] = d/damount.
+ * If grad_img != NULL, `gy_scratch` ([B,3,H,W] floats) must be given: the masked upstream gradient
+ * g*[0<=y<=1] is staged there and the transposed stencil is gathered from it in a second pass.
+ */
+int aisp_sharpen_bwd(const float* img, const float* grad_out, const float* params, const int32_t* ops,
+                     int B, int H, int W, float* grad_params, float* grad_img, float* gy_scratch,
+                     void* scratch, size_t scratch_bytes, void* stream);
+
+/*
+ * Non-local-means denoise, gray-distance variant with 11x11 search / 5x5 patch and circular
+ * boundaries (DenoiseFilter.process isp/filters.py:582-586 -> NonLocalMeansGray
+ * isp/denoise.py:93-119, BoxFilter :46-65, rgb_to_luminance :11-17).
+ *   dout_dh  [B,3,H,W] or NULL.  When given, the kernel also writes d out / d h per pixel and
+ *            channel (clamp mask folded in), the closed form of SURVEY.md §8a row A11, so that the
+ *            backward w.r.t. h is a single dot product instead of a second 121-shift pass.
+ * Samples whose op is not NLM are skipped.
+ */
+int aisp_nlm_fwd(const float* img, float* out, const float* params, const int32_t* ops,
+                 int B, int H, int W, float* dout_dh, void* stream);
+
+/*
+ * Backward of NLM w.r.t. h:  grad_params[b,0] = sum_{c,y,x} grad_out * dout_dh.
+ * grad_img is not implemented for NLM (not needed by training, train.py:255): passing a non-NULL
+ * grad_img returns AISP_ERR_UNSUPPORTED.
+ */
+int aisp_nlm_bwd(const float* grad_out, const float* dout_dh, const int32_t* ops, int B, int H, int W,
+                 float* grad_params, float* grad_img, void* scratch, size_t scratch_bytes, void* stream);
+
+/*
+ * Apply the selected filter of each sample: the B200 form of agent.py:103-116,154, where the
+ * reference runs all 10 filters on the whole batch, stacks [B,10,3,H,W] and keeps one of ten.
+ * Issues the three family kernels back to back on `stream` (no host sync; graph-capturable);
+ * every sample is processed by exactly one of them.  clip as in aisp_pointwise_fwd.
+ */
+int aisp_select_apply_fwd(const float* img, float* out, const float* params, const int32_t* ops,
+                          int B, int H, int W, int clip, float* nlm_dout_dh, void* stream);
+
+int aisp_select_apply_bwd(const float* img, const float* grad_out, const float* params, const int32_t* ops,
+                          int B, int H, int W, int clip, const float* nlm_dout_dh, float* grad_params,
+                          float* grad_img, float* gy_scratch, void* scratch, size_t scratch_bytes,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AISP_B200_H */

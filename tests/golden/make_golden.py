@@ -112,8 +112,70 @@ def select_golden(ref):
     return out
 
 
+def small_agent_cfg(cfg_cls, base):
+    """A narrow Agent (about 25k parameters) so that its state_dict fits in a fixture."""
+    small = cfg_cls(base)
+    small.feature_extractor_dims = 64
+    small.base_channels = 4
+    small.fc1_size = 16
+    small.dropout_keep_prob = 1.0  # no dropout: keeps train mode free of device-specific RNG
+    return small
+
+
+def agent_golden(ref):
+    """Reference Agent.forward (+ backward) on a narrow Agent: weights, inputs, outputs, gradients."""
+    out = {}
+    A = ref.agent
+    cfg = small_agent_cfg(type(ref.cfg), ref.cfg)
+    torch.manual_seed(11)
+    agent = A.Agent(cfg, shape=(16, 64, 64), device="cpu")
+    # give every BatchNorm non-trivial running stats / affine so that eval mode is not degenerate
+    g = torch.Generator().manual_seed(12)
+    for m in agent.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+    for k, v in agent.state_dict().items():
+        out["sd." + k] = v.numpy()
+    B = 4
+    x = cases.edge_image(B, 32, 32, seed=7, in_range=True)
+    z = torch.rand((B, cfg.z_dim), generator=g)
+    states = torch.zeros((B, cfg.num_state_dim))
+    states[:, 2] = torch.tensor([0.0, 2.0, 4.0, 1.0])
+    states[1, 3 + 4] = 1.0
+    gout = cases.grad_out(x.shape, seed=7)
+    out["x"], out["z"], out["states"], out["gout"] = x.numpy(), z.numpy(), states.numpy(), gout.numpy()
+
+    def run(tag, train, forced):
+        agent.train(train)
+        agent.zero_grad(set_to_none=True)
+        (xo, ns, sur, pen), dbg, _ = agent((x, z, states), 0.25, None, forced)
+        loss = (xo * gout).sum() + sur.sum() + pen.sum()
+        loss.backward()
+        out[f"{tag}.x"] = xo.detach().numpy()
+        out[f"{tag}.new_states"] = ns.detach().numpy()
+        out[f"{tag}.surrogate"] = sur.detach().numpy()
+        out[f"{tag}.penalty"] = pen.detach().numpy()
+        out[f"{tag}.selected"] = dbg["selected_filter"].numpy()
+        out[f"{tag}.pdf0"] = dbg["pdf"].detach().numpy()
+        for name, prm in agent.named_parameters():
+            if prm.grad is not None:
+                out[f"{tag}.grad.{name}"] = prm.grad.numpy().copy()
+            else:
+                out[f"{tag}.nograd.{name}"] = np.zeros(1)
+
+    run("train", True, None)
+    run("eval", False, None)
+    for f in range(len(cfg.filters)):
+        run(f"forced{f}", False, f)
+    return out
+
+
 def main():
     ref = ref_shim.load()
+    a = agent_golden(ref)
+    np.savez_compressed(os.path.join(HERE, "agent.npz"), **a)
+    print("agent.npz", os.path.getsize(os.path.join(HERE, "agent.npz")), "bytes")
     f = filters_golden(ref)
     np.savez_compressed(os.path.join(HERE, "filters.npz"), **f)
     s = select_golden(ref)

@@ -1,0 +1,154 @@
+"""CPU-only checks: the C-ABI library builds/loads and exports every symbol the header declares,
+host-side packing / rejection logic, drop-in class surface and checkpoint-key compatibility.
+No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import isp_oracle as O
+from tests import cases, ref_shim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from adaptiveisp_b200 import _lib
+    if not os.path.isfile(_lib.LIB_PATH):
+        _lib.build()
+    return _lib.lib()
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "aisp_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(aisp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from adaptiveisp_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) == 12
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/aisp_b200.h but not exported"
+    assert set(syms) == set(_lib.SIGNATURES), "ctypes binding and header disagree"
+
+
+def test_library_metadata_calls(lib):
+    assert lib.aisp_version() == 1
+    for op in range(13):
+        assert lib.aisp_op_num_params(op) == O.OP_NPARAMS[op]
+    assert lib.aisp_op_num_params(99) == -1
+    assert lib.aisp_bwd_scratch_bytes(64, 512, 512) == 64 * 128 * 32 * 4
+    assert lib.aisp_bwd_scratch_bytes(0, 512, 512) == 0
+    assert b"NULL" in lib.aisp_status_string(-1)
+    # argument validation happens before any CUDA call, so it is checkable without a GPU
+    assert lib.aisp_pointwise_fwd(None, None, None, None, None, 1, 8, 8, 1, 1, None) == -1
+    buf = (ctypes.c_float * 16)()
+    p = ctypes.addressof(buf)
+    assert lib.aisp_pointwise_fwd(p, p + 4, p, p, None, 0, 8, 8, 1, 1, None) == -2
+    assert lib.aisp_pointwise_fwd(p, p + 4, p, p, None, 1, 8, 8, 9, 1, None) == -2
+    assert lib.aisp_pointwise_fwd(p, p, p, p, None, 1, 2, 2, 1, 1, None) == -4       # in-place refused
+    assert lib.aisp_pointwise_bwd(p, p, p, p, 1, 2, 2, 1, p, None, p, 4, None) == -3  # scratch too small
+    assert lib.aisp_nlm_bwd(p, p, p, 1, 2, 2, p, p, p, 1 << 20, None) == -4           # NLM d/dimg unsupported
+
+
+def test_op_codes_shared_between_header_oracle_and_host():
+    from adaptiveisp_b200 import functional as AF
+    text = open(os.path.join(ROOT, "include", "aisp_b200.h")).read()
+    enum = dict((k, int(v)) for k, v in re.findall(r"AISP_OP_([A-Z0-9_]+)\s*=\s*(-?\d+)", text))
+    for name, code in [("EXPOSURE", O.OP_EXPOSURE), ("GAMMA", O.OP_GAMMA), ("CCM", O.OP_CCM),
+                       ("SHARPEN", O.OP_SHARPEN), ("NLM", O.OP_NLM), ("TONE", O.OP_TONE),
+                       ("CONTRAST", O.OP_CONTRAST), ("SATPLUS", O.OP_SATPLUS), ("WNB", O.OP_WNB), ("WB", O.OP_WB),
+                       ("USM", O.OP_USM), ("COLOR", O.OP_COLOR), ("SHARPEN_V2", O.OP_SHARPEN_V2)]:
+        assert enum[name] == code == getattr(AF, "OP_" + name)
+    assert tuple(O.OP_NPARAMS[i] for i in range(13)) == AF.NUM_PARAMS
+
+
+def test_pack_params_layouts():
+    from adaptiveisp_b200 import functional as AF
+    for op in cases.ALL_OPS:
+        _, p = cases.params_for(op, 3)
+        row = AF.pack_params(p, O.OP_NPARAMS[op])
+        assert row.shape == (3, 24)
+        np.testing.assert_array_equal(row[:, :O.OP_NPARAMS[op]].numpy(), cases.flat(op, p).numpy())
+        assert float(row[:, O.OP_NPARAMS[op]:].abs().sum()) == 0.0
+
+
+def test_cpu_tensors_are_rejected_not_converted():
+    from adaptiveisp_b200 import AispError, filters
+    from adaptiveisp_b200.config import make_cfg
+    flt = filters.GammaFilter(make_cfg())
+    with pytest.raises(AispError, match="no CPU path"):
+        flt.process(torch.zeros((1, 3, 4, 4)), torch.ones((1, 1)))
+
+
+def test_dropin_class_surface_and_regressors():
+    """Same class names / short names / parameter counts / regressor values as the reference."""
+    from adaptiveisp_b200 import filters as F
+    from adaptiveisp_b200.config import make_cfg
+    cfg = make_cfg()
+    expect = {"ExposureFilter": ("E", 1), "GammaFilter": ("G", 1), "ImprovedWhiteBalanceFilter": ("W", 3),
+              "ColorFilter": ("C", 24), "ToneFilter": ("T", 8), "ToneFilterV2": ("T", 8), "ContrastFilter": ("Ct", 1),
+              "WNBFilter": ("BW", 1), "SaturationPlusFilter": ("S+", 1), "DenoiseFilter": ("NLM", 1),
+              "SharpenUSMFilter": ("USM", 2), "SharpenFilter": ("Shr", 1), "SharpenFilterV2": ("Shr", 1),
+              "CCMFilter": ("CCM", 9)}
+    for name, (short, n) in expect.items():
+        f = getattr(F, name)(cfg, predict=True)
+        assert f.get_short_name() == short and f.get_num_filter_parameters() == n
+        assert f.get_num_mask_parameters() == 6 and f.channels == 3 and not f.use_masking()
+        assert sorted(k for k, _ in f.named_parameters()) == [
+            "fc1.bias", "fc1.weight", "fc_filter.bias", "fc_filter.weight", "fc_mask.bias", "fc_mask.weight"]
+        feat = cases.features(f.OP, 5, seed=2)
+        got = f.filter_param_regressor(feat)
+        want = O.regress(f.OP, feat)
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=1e-7)
+
+
+def test_agent_state_dict_keys_match_reference_checkpoint_layout(tmp_path):
+    from adaptiveisp_b200.agent import Agent
+    from adaptiveisp_b200.config import make_cfg
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "agent.npz")))
+    ref_keys = sorted(k[3:] for k in g if k.startswith("sd."))
+    cfg = make_cfg(feature_extractor_dims=64, base_channels=4, fc1_size=16, dropout_keep_prob=1.0)
+    agent = Agent(cfg, shape=(16, 64, 64), device="cpu")
+    assert sorted(agent.state_dict().keys()) == ref_keys
+    for k, v in agent.state_dict().items():
+        assert tuple(v.shape) == tuple(g["sd." + k].shape), k
+
+
+def test_agent_selection_logic_bit_exact_on_cpu(golden_select):
+    from adaptiveisp_b200 import agent as A
+    G = golden_select
+    pdf, u = torch.from_numpy(G["pdf"]), torch.from_numpy(G["u"])
+    ids = A.pdf_sample(pdf, u)
+    np.testing.assert_array_equal(ids.numpy(), G["ids_sample"])
+    np.testing.assert_array_equal(A.one_hot(10, ids.to(torch.int64)).numpy(), G["one_hot"])
+    assert int(ids.min()) == -1  # u == 0 row: all-zero one-hot, as in the reference
+    assert int(A.one_hot(10, ids.to(torch.int64))[int(ids.argmin())].sum()) == 0
+
+
+def test_lod_batch_shape_and_letterbox():
+    x = cases.lod_batch(3, 48, 48, seed=1)
+    assert x.shape == (3, 3, 48, 48) and x.dtype == torch.float32
+    assert float(x[:, :, :8].abs().max()) == 0.0 and float(x[:, :, 40:].abs().max()) == 0.0
+    assert float(x.max()) <= 1.0 and float(x.min()) >= 0.0
+    np.testing.assert_allclose((x * 255).round().numpy(), (x * 255).numpy(), atol=1e-4)  # k/255 lattice
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not present")
+def test_reference_config_accepts_dropin_classes():
+    """config.py's star-import seam: the reference cfg object drives the drop-in classes unchanged."""
+    from adaptiveisp_b200 import filters as F
+    ref = ref_shim.load()
+    for cls in ref.cfg.filters:
+        mine = getattr(F, cls.__name__)(ref.cfg, predict=True)
+        theirs = cls(ref.cfg, predict=True)
+        assert mine.get_short_name() == theirs.get_short_name()
+        assert {k: tuple(v.shape) for k, v in mine.state_dict().items()} == \
+               {k: tuple(v.shape) for k, v in theirs.state_dict().items()}
