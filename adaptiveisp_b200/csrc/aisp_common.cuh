@@ -97,10 +97,15 @@ __device__ inline void derive_consts(int op, const float* raw, float* c) {
         break;
     }
     case AISP_OP_COLOR: {  // per-channel curves              isp/filters.py:297,302
-        float s[3] = {0.f, 0.f, 0.f};
-        for (int k = 0; k < 8; ++k)
-            for (int ch = 0; ch < 3; ++ch) { c[3 * k + ch] = raw[3 * k + ch]; s[ch] += raw[3 * k + ch]; }
-        for (int ch = 0; ch < 3; ++ch) c[24 + ch] = 8.0f / (s[ch] + 1e-30f);
+        // torch.sum over the strided knot dim runs 4 interleaved accumulators (k % 4) and combines
+        // them left to right; same order here so that saturated pixels hit the same side of 1.0
+        for (int k = 0; k < 24; ++k) c[k] = raw[k];
+        for (int ch = 0; ch < 3; ++ch) {
+            float a4[4];
+            for (int j = 0; j < 4; ++j) a4[j] = raw[3 * j + ch] + raw[3 * (j + 4) + ch];
+            const float s = ((a4[0] + a4[1]) + a4[2]) + a4[3];
+            c[24 + ch] = 8.0f / (s + 1e-30f);
+        }
         break;
     }
     case AISP_OP_USM: {  // 5-tap gaussian and its sigma-derivative   isp/sharpen.py:15-23

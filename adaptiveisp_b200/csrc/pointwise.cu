@@ -14,6 +14,12 @@ namespace aisp {
 // =============================================================================================
 // per-pixel forward math (in place).  c = derived constants of this step.
 // =============================================================================================
+// NOTE on rounding: this file is compiled with -fmad=false and the forward expressions below keep
+// the reference's operation order (each product rounded, then added, as ATen does on the CPU).
+// Saturated pixels (x == 1.0) land on y == 1.0 +- 1 ulp for the curve / CCM / desaturation /
+// saturation filters, and the clamp backward of Filter.forward passes the gradient iff y <= 1: only
+// bit-identical forward arithmetic reproduces the reference's gradient mask on those pixels.
+// Explicit fmaf() is used only in gradient accumulators, where order is free.
 __device__ __forceinline__ float lum_isp(float r, float g, float b) {  // isp/filters.py:12-14
     return (0.27f * r + 0.67f * g) + 0.06f * b;
 }
@@ -24,7 +30,7 @@ __device__ __forceinline__ float curve8(float x, const float* c, int stride) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         float seg = fminf(fmaxf(x - 0.125f * (float)k, 0.f), 0.125f);
-        acc = fmaf(seg, c[k * stride], acc);
+        acc = acc + seg * c[k * stride];
     }
     return acc;
 }
@@ -121,9 +127,9 @@ __device__ __forceinline__ void fwd_step(int op, const float* __restrict__ c, fl
 #pragma unroll
         for (int i = 0; i < NPX; ++i) {
             const float r = R[i], g = G[i], b = B[i];
-            R[i] = fmaf(b, m[2], fmaf(g, m[1], r * m[0]));
-            G[i] = fmaf(b, m[5], fmaf(g, m[4], r * m[3]));
-            B[i] = fmaf(b, m[8], fmaf(g, m[7], r * m[6]));
+            R[i] = (r * m[0] + g * m[1]) + b * m[2];
+            G[i] = (r * m[3] + g * m[4]) + b * m[5];
+            B[i] = (r * m[6] + g * m[7]) + b * m[8];
         }
         break;
     }
@@ -206,7 +212,7 @@ struct PwBwd<AISP_OP_EXPOSURE> {
                                               float& gb, int clip, float* acc) {
         const float s = c[0];
         AISP_MASK_CLIP(r * s, g * s, b * s)
-        acc[0] += gr * r + gg * g + gb * b;
+        acc[0] = fmaf(gr, r, fmaf(gg, g, fmaf(gb, b, acc[0])));
         if (GIMG) { gr *= s; gg *= s; gb *= s; }
     }
 };
@@ -222,7 +228,7 @@ struct PwBwd<AISP_OP_GAMMA> {
         const float lr = __log2f(xr), lg = __log2f(xg), lb = __log2f(xb);
         const float yr = exp2f(p * lr), yg = exp2f(p * lg), yb = exp2f(p * lb);
         AISP_MASK_CLIP(yr, yg, yb)
-        acc[0] += gr * yr * lr + gg * yg * lg + gb * yb * lb;  // x ln2 in finalize
+        acc[0] = fmaf(gr * yr, lr, fmaf(gg * yg, lg, fmaf(gb * yb, lb, acc[0])));  // x ln2 in finalize
         if (GIMG) {  // p * x^(p-1), only where the min-clamp passed (x >= 0.001, inclusive)
             gr = (r >= 0.001f) ? gr * p * __fdividef(yr, xr) : 0.f;
             gg = (g >= 0.001f) ? gg * p * __fdividef(yg, xg) : 0.f;
@@ -238,7 +244,7 @@ struct PwBwd<AISP_OP_WB> {
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
                                               float& gb, int clip, float* acc) {
         AISP_MASK_CLIP(r * c[0], g * c[1], b * c[2])
-        acc[0] += gr * r; acc[1] += gg * g; acc[2] += gb * b;
+        acc[0] = fmaf(gr, r, acc[0]); acc[1] = fmaf(gg, g, acc[1]); acc[2] = fmaf(gb, b, acc[2]);
         if (GIMG) { gr *= c[0]; gg *= c[1]; gb *= c[2]; }
     }
 };
@@ -249,9 +255,9 @@ struct PwBwd<AISP_OP_CCM> {
     template <bool GIMG>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
                                               float& gb, int clip, float* acc) {
-        const float yr = fmaf(b, c[2], fmaf(g, c[1], r * c[0]));
-        const float yg = fmaf(b, c[5], fmaf(g, c[4], r * c[3]));
-        const float yb = fmaf(b, c[8], fmaf(g, c[7], r * c[6]));
+        const float yr = (r * c[0] + g * c[1]) + b * c[2];
+        const float yg = (r * c[3] + g * c[4]) + b * c[5];
+        const float yb = (r * c[6] + g * c[7]) + b * c[8];
         AISP_MASK_CLIP(yr, yg, yb)
         acc[0] = fmaf(gr, r, acc[0]); acc[1] = fmaf(gr, g, acc[1]); acc[2] = fmaf(gr, b, acc[2]);
         acc[3] = fmaf(gg, r, acc[3]); acc[4] = fmaf(gg, g, acc[4]); acc[5] = fmaf(gg, b, acc[5]);
@@ -274,7 +280,7 @@ __device__ __forceinline__ void curve8_bwd(float x, const float* c, int stride, 
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         seg[k] = fminf(fmaxf(x - 0.125f * (float)k, 0.f), 0.125f);
-        sum = fmaf(seg[k], c[k * stride], sum);
+        sum = sum + seg[k] * c[k * stride];
     }
     const float y = sum * sc;
     if (clip) g *= pass01(y);
@@ -332,7 +338,7 @@ struct PwBwd<AISP_OP_CONTRAST> {
         const float inv = 1.0f / den;
         const float cr = r * inv * cl, cg = g * inv * cl, cb = b * inv * cl;
         AISP_MASK_CLIP(ip * r + p * cr, ip * g + p * cg, ip * b + p * cb)
-        acc[0] += gr * (cr - r) + gg * (cg - g) + gb * (cb - b);
+        acc[0] = fmaf(gr, cr - r, fmaf(gg, cg - g, fmaf(gb, cb - b, acc[0])));
         if (GIMG) {
             const float ratio = cl * inv;
             const float dratio = (0.5f * AISP_PIF * sn * den - cl) * inv * inv;
@@ -354,7 +360,7 @@ struct PwBwd<AISP_OP_WNB> {
         const float p = c[0], ip = 1.f - p;
         const float l = lum_isp(r, g, b);
         AISP_MASK_CLIP(ip * r + p * l, ip * g + p * l, ip * b + p * l)
-        acc[0] += gr * (l - r) + gg * (l - g) + gb * (l - b);
+        acc[0] = fmaf(gr, l - r, fmaf(gg, l - g, fmaf(gb, l - b, acc[0])));
         if (GIMG) {
             const float s = p * (gr + gg + gb);
             gr = ip * gr + s * 0.27f;
@@ -376,7 +382,7 @@ struct PwBwd<AISP_OP_SATPLUS> {
         HsvState st;
         satplus_full(r, g, b, fr, fg, fb, st);
         AISP_MASK_CLIP(r * ip + fr * p, g * ip + fg * p, b * ip + fb * p)
-        acc[0] += gr * (fr - r) + gg * (fg - g) + gb * (fb - b);
+        acc[0] = fmaf(gr, fr - r, fmaf(gg, fg - g, fmaf(gb, fb - b, acc[0])));
         if (GIMG) {
             // reverse sweep through hsv2rgb -> enhanced saturation -> rgb2hsv -> leading clip
             float cr = gr * ip, cg = gg * ip, cb = gb * ip;
