@@ -152,13 +152,13 @@ __device__ inline void finalize_grads(int op, const double* a, const float* c, c
             for (int k = 0; k < 3; ++k) gp[3 * i + k] = (float)((a[3 * i + k] - dot) * (double)c[9 + i]);
         }
         break;
-    case AISP_OP_TONE:  // a[k] = sum gy*seg_k ; a[8] = sum gy*y
-        for (int k = 0; k < 8; ++k) gp[k] = (float)((double)c[8] * (a[k] - a[8] * 0.125));
+    case AISP_OP_TONE:  // a[k] = 8 * sum gy*seg_k ; a[8] = sum gy*y ; dy/dp_k = sc*seg_k - y*sc/8
+        for (int k = 0; k < 8; ++k) gp[k] = (float)((double)c[8] * 0.125 * (a[k] - a[8]));
         break;
     case AISP_OP_COLOR:  // a[3k+ch], a[24+ch]
         for (int k = 0; k < 8; ++k)
             for (int ch = 0; ch < 3; ++ch)
-                gp[3 * k + ch] = (float)((double)c[24 + ch] * (a[3 * k + ch] - a[24 + ch] * 0.125));
+                gp[3 * k + ch] = (float)((double)c[24 + ch] * 0.125 * (a[3 * k + ch] - a[24 + ch]));
         break;
     case AISP_OP_USM:  // a0 = sum gy*(d blur/d sigma), a1 = sum gy*(x - blur)
         gp[0] = (float)(-(double)raw[1] * a[0]);

@@ -25,14 +25,26 @@ __device__ __forceinline__ float lum_isp(float r, float g, float b) {  // isp/fi
 }
 
 __device__ __forceinline__ float curve8(float x, const float* c, int stride) {
-    // sum_k clip(x - k/8, 0, 1/8) * p_k, k ascending (isp/filters.py:342-344)
+    // 8 * sum_k clip(x - k/8, 0, 1/8) * p_k, k ascending (isp/filters.py:342-344).
+    // clip(x - k/8, 0, 1/8) == sat(8x - k) / 8 exactly (power-of-two scaling commutes with every
+    // rounding), so each knot is one FFMA.SAT + FMUL + FADD on the FMA pipe instead of
+    // FADD + 2 FMNMX on the half-rate ALU pipe; the factor 8 is folded into the scale (c[8]/8).
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        float seg = fminf(fmaxf(x - 0.125f * (float)k, 0.f), 0.125f);
-        acc = acc + seg * c[k * stride];
+        const float u = __saturatef(fmaf(x, 8.0f, -(float)k));
+        acc = acc + u * c[k * stride];
     }
     return acc;
+}
+
+// correctly rounded a / 6 without the IEEE-division slow path (Markstein: q' = RN(q + r*y) with
+// y = RN(1/6), q faithful); keeps floor(6*h) on the reference's side of every sextant boundary
+__device__ __forceinline__ float div6(float a) {
+    const float y = 0.16666667163372039794921875f;
+    const float q = a * y;
+    const float r = fmaf(-6.0f, q, a);
+    return fmaf(r, y, q);
 }
 
 // HSV round trip of SaturationPlusFilter (isp/filters.py:445-560) for one pixel.
@@ -53,17 +65,19 @@ __device__ __forceinline__ void satplus_full(float r, float g, float b, float& f
     float hue = 0.f, num = 0.f;
     int branch = -1;
     // ordered overwrites: B first, then G, then R -> R wins ties (isp/filters.py:456-464)
-    if (b == mx) { num = r - g; hue = 4.0f + num / d; branch = 2; }
-    if (g == mx) { num = b - r; hue = 2.0f + num / d; branch = 1; }
-    if (r == mx) {
-        num = g - b;
-        float q = num / d;               // |q| <= 1, so python-style q % 6 is q or q + 6
-        hue = (q < 0.f) ? q + 6.0f : q;
-        branch = 0;
-    }
+    float base = 0.f;
+    if (b == mx) { num = r - g; base = 4.0f; branch = 2; }
+    if (g == mx) { num = b - r; base = 2.0f; branch = 1; }
+    if (r == mx) { num = g - b; base = 0.0f; branch = 0; }
+    // one correctly rounded division for the winning branch (|q| <= 1): hue must land on the
+    // reference's side of integer values, which decide the sextant and the gradient routing
+    const float q = __fdiv_rn(num, d);
+    hue = (branch == 0) ? ((q < 0.f) ? q + 6.0f : q)   // python-style q % 6
+                        : base + q;
     if (mn == mx) { hue = 0.f; branch = -1; }
-    hue = hue / 6.0f;
-    float sat = (mx - mn) / (mx + 1e-8f);
+    hue = div6(hue);
+    // saturation only feeds continuous expressions: fast reciprocal is enough
+    float sat = __fdividef(mx - mn, mx + 1e-8f);
     const bool satzero = (mx == 0.f);
     if (satzero) sat = 0.f;
     // enhanced saturation (isp/filters.py:552)
@@ -134,7 +148,7 @@ __device__ __forceinline__ void fwd_step(int op, const float* __restrict__ c, fl
         break;
     }
     case AISP_OP_TONE: {
-        const float sc = c[8];
+        const float sc = c[8] * 0.125f;  // exact: undoes the factor 8 carried by curve8()
 #pragma unroll
         for (int i = 0; i < NPX; ++i) {
             R[i] = curve8(R[i], c, 1) * sc;
@@ -146,9 +160,9 @@ __device__ __forceinline__ void fwd_step(int op, const float* __restrict__ c, fl
     case AISP_OP_COLOR: {
 #pragma unroll
         for (int i = 0; i < NPX; ++i) {
-            R[i] = curve8(R[i], c + 0, 3) * c[24];
-            G[i] = curve8(G[i], c + 1, 3) * c[25];
-            B[i] = curve8(B[i], c + 2, 3) * c[26];
+            R[i] = curve8(R[i], c + 0, 3) * (c[24] * 0.125f);
+            G[i] = curve8(G[i], c + 1, 3) * (c[25] * 0.125f);
+            B[i] = curve8(B[i], c + 2, 3) * (c[26] * 0.125f);
         }
         break;
     }
@@ -271,29 +285,28 @@ struct PwBwd<AISP_OP_CCM> {
     }
 };
 
-// one channel of a curve filter: returns y (unscaled sum), accumulates gy*seg_k, returns slope sum
+// one channel of a curve filter.  u_k = sat(8x - k) = 8 * clip(x - k/8, 0, 1/8) (see curve8);
+// accumulates g*u_k (8x the segment sums, undone in finalize_grads) and g*y.
 template <bool GIMG>
 __device__ __forceinline__ void curve8_bwd(float x, const float* c, int stride, float sc, float& g, int clip,
                                            float* acc, int astride, float& yacc) {
-    float seg[8];
+    float u[8], v[8];
     float sum = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        seg[k] = fminf(fmaxf(x - 0.125f * (float)k, 0.f), 0.125f);
-        sum = sum + seg[k] * c[k * stride];
+        v[k] = fmaf(x, 8.0f, -(float)k);
+        u[k] = __saturatef(v[k]);
+        sum = sum + u[k] * c[k * stride];
     }
-    const float y = sum * sc;
+    const float y = sum * (sc * 0.125f);
     if (clip) g *= pass01(y);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k * astride] = fmaf(g, seg[k], acc[k * astride]);
+    for (int k = 0; k < 8; ++k) acc[k * astride] = fmaf(g, u[k], acc[k * astride]);
     yacc = fmaf(g, y, yacc);
     if (GIMG) {  // clamp backward is inclusive at both ends: on a knot two segments pass
         float slope = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float t = x - 0.125f * (float)k;
-            slope += (t >= 0.f && t <= 0.125f) ? c[k * stride] : 0.f;
-        }
+        for (int k = 0; k < 8; ++k) slope += (v[k] >= 0.f && v[k] <= 1.0f) ? c[k * stride] : 0.f;
         g = g * sc * slope;
     }
 }

@@ -5,8 +5,9 @@
 //   USM         y = clip(x + (x - G_sigma*x)*a)     isp/sharpen.py:84-102   (5x5, reflect padding)
 //
 // CTA <-> (sample, 128x16 tile); the tile plus a 2-px halo of all three planes is staged in shared
-// memory once (border rule applied while staging), each thread produces a 4x2 block per plane from
-// registers (separable 5-tap passes for USM), so HBM sees ~24 B/px fwd and ~24 B/px bwd.
+// memory once with 128-bit row copies (border rule applied while staging), each thread produces a
+// 4x2 block per plane from registers (separable 5-tap passes for USM), so HBM sees ~24 B/px fwd and
+// ~24 B/px bwd; halo rows/columns re-read by neighbouring CTAs are L2 hits.
 #include "aisp_common.cuh"
 
 namespace aisp {
@@ -22,20 +23,33 @@ __device__ __forceinline__ int reflect_clamp(int i, int n) {
     return min(max(i, 0), n - 1);
 }
 
-// stage tile + halo of one sample (3 planes) into shared memory
+// stage tile + halo of one sample (3 planes) into shared memory: a warp copies whole rows, one
+// 128-bit load + one 128-bit shared store per lane for the 128 interior columns, and lanes 0..3
+// fetch the four halo columns; the border rule (reflect, clamped) is applied on the way in.
 __device__ __forceinline__ void stage_tile(const float* __restrict__ img, float (*sm)[kSmH][kSmW], int H, int W,
-                                           int x0, int y0) {
-    constexpr int CW = kShTileW + 2 * kHalo;  // 132 columns actually needed
-    for (int e = threadIdx.x; e < 3 * kSmH * CW; e += kThreads) {
-        const int ch = e / (kSmH * CW);
-        const int rem = e - ch * (kSmH * CW);
-        const int row = rem / CW, col = rem - row * CW;
-        const int gy = reflect_clamp(y0 - kHalo + row, H);
-        const int gx = reflect_clamp(x0 - kHalo + col, W);
-        sm[ch][row][col + kColOff - kHalo] = __ldg(img + ((size_t)ch * H + gy) * W + gx);
+                                           int x0, int y0, bool vec) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gx = x0 + 4 * lane;
+    const bool own_vec = vec && (gx + 3 < W);
+    const int hc = (lane < 2) ? lane - 2 : kShTileW - 2 + lane;   // halo column of lanes 0..3: -2,-1,128,129
+    const int hx = reflect_clamp(x0 + hc, W);
+#pragma unroll 4
+    for (int rr = warp; rr < 3 * kSmH; rr += kWarps) {
+        const int ch = rr / kSmH, row = rr - ch * kSmH;
+        const float* src = img + ((size_t)ch * H + reflect_clamp(y0 - kHalo + row, H)) * W;
+        float4 v;
+        if (own_vec) {
+            v = __ldg(reinterpret_cast<const float4*>(src + gx));
+        } else {
+            v.x = __ldg(src + reflect_clamp(gx, W));
+            v.y = __ldg(src + reflect_clamp(gx + 1, W));
+            v.z = __ldg(src + reflect_clamp(gx + 2, W));
+            v.w = __ldg(src + reflect_clamp(gx + 3, W));
+        }
+        *reinterpret_cast<float4*>(&sm[ch][row][kColOff + 4 * lane]) = v;
+        if (lane < 4) sm[ch][row][kColOff + hc] = __ldg(src + hx);
     }
 }
-
 
 __device__ __forceinline__ void load_consts(const float* __restrict__ params, int b, int op, float* sc /*smem*/) {
     if (threadIdx.x == 0) {
@@ -128,7 +142,7 @@ sharpen_kernel(const float* __restrict__ img, const float* __restrict__ gout, fl
     const int x0 = blockIdx.x * kShTileW, y0 = blockIdx.y * kShTileH;
     const size_t base = (size_t)b * 3 * H * W;
     load_consts(params, b, op, sc);
-    stage_tile(img + base, sm, H, W, x0, y0);
+    stage_tile(img + base, sm, H, W, x0, y0, vec != 0);
     __syncthreads();
 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -305,7 +319,7 @@ cudaError_t launch_finalize(const float* partial, int nrows, const float* params
 cudaError_t launch_sharpen_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H,
                                int W, cudaStream_t st) {
     dim3 grid((W + kShTileW - 1) / kShTileW, (H + kShTileH - 1) / kShTileH, B);
-    const int vec = ((W & 3) == 0) && al16(out);
+    const int vec = ((W & 3) == 0) && al16(img) && al16(out);
     sharpen_kernel<false, false><<<grid, kThreads, 0, st>>>(img, nullptr, out, params, ops, H, W, vec, nullptr);
     return cudaGetLastError();
 }
@@ -314,7 +328,7 @@ cudaError_t launch_sharpen_bwd(const float* img, const float* gout, const float*
                                int H, int W, float* grad_params, float* grad_img, float* gy_scratch, float* partial,
                                cudaStream_t st) {
     dim3 grid((W + kShTileW - 1) / kShTileW, (H + kShTileH - 1) / kShTileH, B);
-    const int vec = ((W & 3) == 0) && al16(gout) && (!grad_img || al16(gy_scratch));
+    const int vec = ((W & 3) == 0) && al16(img) && al16(gout) && (!grad_img || al16(gy_scratch));
     if (grad_img)
         sharpen_kernel<true, true><<<grid, kThreads, 0, st>>>(img, gout, gy_scratch, params, ops, H, W, vec, partial);
     else
