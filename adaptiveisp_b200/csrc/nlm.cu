@@ -31,12 +31,12 @@ __device__ __forceinline__ int wrap(int i, int n) {
 }
 __device__ __forceinline__ float sqrt_approx(float x) {
     float y;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
-    asm("ex2.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 

@@ -143,7 +143,10 @@ class Filter(nn.Module):
             filter_parameters = specified_parameter
             mask_parameters = torch.zeros(1, self.get_num_mask_parameters(), dtype=torch.float32)
         debug_info = {"filter_parameters": self._debug(filter_parameters)}
-        self.mask_parameters = mask_parameters
+        # same values as the reference's side effect; detached because the mask is never used
+        # (isp/filters.py:161-173) and a live reference would pin the whole autograd graph of this
+        # call (and its AccumulateGrad nodes) between iterations, which breaks CUDA-graph capture
+        self.mask_parameters = mask_parameters.detach()
         self.mask = self.get_mask(img, mask_parameters)
         debug_info["mask"] = self.mask[0]
         low_res_output = self._filter_apply(img, filter_parameters, clip=True)

@@ -266,31 +266,55 @@ def run_b200(args):
     for f in flts:
         f.train()
 
-    def e2e_step():
-        x = host_img.to(dev, non_blocking=True)
-        ft = host_feat.to(dev, non_blocking=True)
+    from adaptiveisp_b200.pipeline import GraphedHostLoop, HostStagedLoop
+
+    def isp_step(x, ft):
         last = None
         for f in flts:
             y, _, _ = f(x, ft)
             y.backward(gout)
             last = y
-        host_out.copy_(last.detach(), non_blocking=True)
+        return last
+
+    graphed = GraphedHostLoop(lambda x, ft: isp_step(x, ft).detach(), (img, feats * 0.05), modules=flts)
+
+    def e2e_run(nsteps, mode):
+        """`nsteps` steps, each uploading the image batch + features from pinned host memory and
+        downloading one output batch.
+          "graph"  : CUDA-graph replay of the step + double-buffered copies (GraphedHostLoop)
+          "staged" : eager class API, copies of neighbouring steps overlapped (HostStagedLoop)
+          "sync"   : eager, the reference's synchronous order (train.py:255, :378-381)"""
+        if mode == "graph":
+            graphed.run(((host_img, host_feat) for _ in range(nsteps)), host_out)
+        elif mode == "staged":
+            loop = HostStagedLoop(dev, depth=2)
+            for x, ft in loop.stage((host_img, host_feat) for _ in range(nsteps)):
+                loop.fetch(isp_step(x, ft).detach(), host_out)
+            loop.drain()
+        else:
+            for _ in range(nsteps):
+                x = host_img.to(dev, non_blocking=True)
+                ft = host_feat.to(dev, non_blocking=True)
+                host_out.copy_(isp_step(x, ft).detach(), non_blocking=True)
 
     e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    tw2 = time.time()
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    tw3 = time.time()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * px_step * e2e_steps / 1e6 / (float(t.item()) / 1e3)
+    e2e_vals = {}
+    win = []
+    for staged in ("graph", "staged", "sync"):
+        e2e_run(3, staged)
+        barrier()
+        tw2 = time.time()
+        e0.record()
+        e2e_run(e2e_steps, staged)
+        e1.record()
+        barrier()
+        tw3 = time.time()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_vals[staged] = world * px_step * e2e_steps / 1e6 / (float(t.item()) / 1e3)
+        win.append((tw2, tw3))
+    e2e_value = e2e_vals["graph"]
     h2d = host_img.numel() * 4 + host_feat.numel() * 4
     d2h = host_out.numel() * 4
 
@@ -326,9 +350,12 @@ def run_b200(args):
             "hbm_frac_excl_nlm": pw_bytes / 1e9 / (pw_ms / 1e3) / peak,
             "kernels": klist,
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps,
+                    "api": "drop-in Filter.forward + .backward() for all 10 filters, replayed as one CUDA graph per "
+                           "step by GraphedHostLoop with double-buffered pinned-host copies",
+                    "value_eager_staged": e2e_vals["staged"], "value_eager_sync": e2e_vals["sync"]},
             "gpu_launches": launches_per_step * args.steps,
-            "clocks": clocks.summary([(tw0, tw1), (tw2, tw3)]),
+            "clocks": clocks.summary([(tw0, tw1)] + win),
         }
         if world == 1 and not args.no_cpu:
             mps, dt, cores = cpu_step(1, 2)
