@@ -23,9 +23,24 @@ __device__ __forceinline__ int reflect_clamp(int i, int n) {
     return min(max(i, 0), n - 1);
 }
 
+// Ampere-style async copies (LDGSTS): global -> shared without a register round trip, so a CTA's
+// whole tile is in flight at once and the staging of one CTA overlaps the arithmetic of its
+// neighbours on the SM.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // stage tile + halo of one sample (3 planes) into shared memory: a warp copies whole rows, one
-// 128-bit load + one 128-bit shared store per lane for the 128 interior columns, and lanes 0..3
-// fetch the four halo columns; the border rule (reflect, clamped) is applied on the way in.
+// 16-byte async copy per lane for the 128 interior columns, and lanes 0..3 fetch the four halo
+// columns; the border rule (reflect, clamped) is applied on the way in.
 __device__ __forceinline__ void stage_tile(const float* __restrict__ img, float (*sm)[kSmH][kSmW], int H, int W,
                                            int x0, int y0, bool vec) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -33,21 +48,17 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ img, float 
     const bool own_vec = vec && (gx + 3 < W);
     const int hc = (lane < 2) ? lane - 2 : kShTileW - 2 + lane;   // halo column of lanes 0..3: -2,-1,128,129
     const int hx = reflect_clamp(x0 + hc, W);
-#pragma unroll 4
     for (int rr = warp; rr < 3 * kSmH; rr += kWarps) {
         const int ch = rr / kSmH, row = rr - ch * kSmH;
         const float* src = img + ((size_t)ch * H + reflect_clamp(y0 - kHalo + row, H)) * W;
-        float4 v;
+        float* dst = &sm[ch][row][kColOff + 4 * lane];
         if (own_vec) {
-            v = __ldg(reinterpret_cast<const float4*>(src + gx));
+            cp_async16(dst, src + gx);
         } else {
-            v.x = __ldg(src + reflect_clamp(gx, W));
-            v.y = __ldg(src + reflect_clamp(gx + 1, W));
-            v.z = __ldg(src + reflect_clamp(gx + 2, W));
-            v.w = __ldg(src + reflect_clamp(gx + 3, W));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp_async4(dst + i, src + reflect_clamp(gx + i, W));
         }
-        *reinterpret_cast<float4*>(&sm[ch][row][kColOff + 4 * lane]) = v;
-        if (lane < 4) sm[ch][row][kColOff + hc] = __ldg(src + hx);
+        if (lane < 4) cp_async4(&sm[ch][row][kColOff + hc], src + hx);
     }
 }
 
@@ -141,16 +152,36 @@ sharpen_kernel(const float* __restrict__ img, const float* __restrict__ gout, fl
     if (!is_sharpen(op)) return;
     const int x0 = blockIdx.x * kShTileW, y0 = blockIdx.y * kShTileH;
     const size_t base = (size_t)b * 3 * H * W;
-    load_consts(params, b, op, sc);
     stage_tile(img + base, sm, H, W, x0, y0, vec != 0);
-    __syncthreads();
+    load_consts(params, b, op, sc);
 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int bx = tx * 4, by = ty * 2;
     const int gx0 = x0 + bx, gy0 = y0 + by;
-    const float f = (op == AISP_OP_USM) ? sc[10] : sc[0];
     const bool vec_ok = vec && (gx0 + 3 < W);  // vec: W % 4 == 0 and 16B-aligned global pointers
     float acc[2] = {0.f, 0.f};
+    // upstream gradient of this thread's 3 x 2 x 4 outputs: requested before the tile has landed
+    float gpre[3][2][4];
+    if (BWD) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int gy = gy0 + r;
+                const size_t off = base + ((size_t)ch * H + gy) * W + gx0;
+                if (gy < H && vec_ok) {
+                    const float4 t = ldg_stream4(gout + off);
+                    gpre[ch][r][0] = t.x; gpre[ch][r][1] = t.y; gpre[ch][r][2] = t.z; gpre[ch][r][3] = t.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        gpre[ch][r][i] = (gy < H && gx0 + i < W) ? gout[off + i] : 0.f;
+                }
+            }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const float f = (op == AISP_OP_USM) ? sc[10] : sc[0];
 
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
@@ -177,13 +208,8 @@ sharpen_kernel(const float* __restrict__ img, const float* __restrict__ gout, fl
                 }
             } else {
                 float g[4];
-                if (vec_ok) {
-                    float4 t = ldg_stream4(gout + off);
-                    g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
-                } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) g[i] = (gx0 + i < W) ? gout[off + i] : 0.f;
-                }
+                for (int i = 0; i < 4; ++i) g[i] = gpre[ch][r][i];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     g[i] *= pass01(y[i]);
