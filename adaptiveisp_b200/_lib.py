@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(CSRC, "libaisp_b200.so")
 
 PSTRIDE = 24
 MAX_STEPS = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/aisp_b200.h one to one
 _P = c_void_p
@@ -31,10 +31,12 @@ SIGNATURES = {
     "aisp_pointwise_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "aisp_sharpen_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "aisp_sharpen_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
-    "aisp_nlm_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
-    "aisp_nlm_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
-    "aisp_select_apply_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
-    "aisp_select_apply_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "aisp_nlm_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "aisp_nlm_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "aisp_nlm_bwd_img": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "aisp_select_apply_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "aisp_select_apply_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_size_t,
+                                      _P]),
 }
 
 _lib = None

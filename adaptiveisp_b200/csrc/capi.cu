@@ -10,7 +10,10 @@ cudaError_t launch_pointwise_bwd(const float*, const float*, const float*, const
 cudaError_t launch_sharpen_fwd(const float*, float*, const float*, const int32_t*, int, int, int, cudaStream_t);
 cudaError_t launch_sharpen_bwd(const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*,
                                float*, float*, cudaStream_t);
-cudaError_t launch_nlm_fwd(const float*, float*, const float*, const int32_t*, int, int, int, float*, cudaStream_t);
+cudaError_t launch_nlm_fwd(const float*, float*, const float*, const int32_t*, int, int, int, float*, float*,
+                           cudaStream_t);
+cudaError_t launch_nlm_bwd_img(const float*, const float*, const float*, const float*, const float*, const int32_t*, int,
+                               int, int, float*, cudaStream_t);
 cudaError_t launch_nlm_bwd(const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*,
                            cudaStream_t);
 int pointwise_rows(int H, int W);
@@ -32,7 +35,7 @@ inline int shape_ok(int B, int H, int W) {
 
 extern "C" {
 
-int aisp_version(void) { return 1; }
+int aisp_version(void) { return 2; }
 
 const char* aisp_status_string(int s) {
     switch (s) {
@@ -98,46 +101,56 @@ int aisp_sharpen_bwd(const float* img, const float* grad_out, const float* param
 }
 
 int aisp_nlm_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,
-                 float* dout_dh, void* stream) {
+                 float* dout_dh, float* wsum, void* stream) {
     if (!img || !out || !params || !ops) return AISP_ERR_NULL;
     if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
     if (img == out) return AISP_ERR_UNSUPPORTED;
-    return (int)launch_nlm_fwd(img, out, params, ops, B, H, W, dout_dh, (cudaStream_t)stream);
+    return (int)launch_nlm_fwd(img, out, params, ops, B, H, W, dout_dh, wsum, (cudaStream_t)stream);
 }
 
 int aisp_nlm_bwd(const float* grad_out, const float* dout_dh, const int32_t* ops, int B, int H, int W,
-                 float* grad_params, float* grad_img, void* scratch, size_t scratch_bytes, void* stream) {
+                 float* grad_params, void* scratch, size_t scratch_bytes, void* stream) {
     if (!grad_out || !dout_dh || !ops || !grad_params || !scratch) return AISP_ERR_NULL;
-    if (grad_img) return AISP_ERR_UNSUPPORTED;
     if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
     if (scratch_bytes < aisp_bwd_scratch_bytes(B, H, W)) return AISP_ERR_SCRATCH;
     return (int)launch_nlm_bwd(grad_out, dout_dh, nullptr, ops, B, H, W, grad_params, (float*)scratch,
                                (cudaStream_t)stream);
 }
 
+int aisp_nlm_bwd_img(const float* img, const float* out, const float* wsum, const float* grad_out,
+                     const float* params, const int32_t* ops, int B, int H, int W, float* grad_img, void* stream) {
+    if (!img || !out || !wsum || !grad_out || !params || !ops || !grad_img) return AISP_ERR_NULL;
+    if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
+    return (int)launch_nlm_bwd_img(img, out, wsum, grad_out, params, ops, B, H, W, grad_img, (cudaStream_t)stream);
+}
+
 int aisp_select_apply_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,
-                          int clip, float* nlm_dout_dh, void* stream) {
+                          int clip, float* nlm_dout_dh, float* nlm_wsum, void* stream) {
     int e = aisp_pointwise_fwd(img, out, params, ops, nullptr, B, H, W, 1, clip, stream);
     if (e) return e;
     e = aisp_sharpen_fwd(img, out, params, ops, B, H, W, stream);
     if (e) return e;
-    return aisp_nlm_fwd(img, out, params, ops, B, H, W, nlm_dout_dh, stream);
+    return aisp_nlm_fwd(img, out, params, ops, B, H, W, nlm_dout_dh, nlm_wsum, stream);
 }
 
-int aisp_select_apply_bwd(const float* img, const float* grad_out, const float* params, const int32_t* ops, int B,
-                          int H, int W, int clip, const float* nlm_dout_dh, float* grad_params, float* grad_img,
-                          float* gy_scratch, void* scratch, size_t scratch_bytes, void* stream) {
-    // grad_img on a heterogeneous batch would need the (unimplemented) NLM image gradient for the
-    // NLM samples; refuse rather than return partially written gradients.
-    if (grad_img && nlm_dout_dh) return AISP_ERR_UNSUPPORTED;
+int aisp_select_apply_bwd(const float* img, const float* out, const float* grad_out, const float* params,
+                          const int32_t* ops, int B, int H, int W, int clip, const float* nlm_dout_dh,
+                          const float* nlm_wsum, float* grad_params, float* grad_img, float* gy_scratch, void* scratch,
+                          size_t scratch_bytes, void* stream) {
+    // the NLM samples of a heterogeneous batch need their stashes: d out/d h for grad_params,
+    // the weight sums (and the forward output) for grad_img
+    // (nlm_dout_dh == NULL: the caller does not need parameter gradients of the NLM samples; their
+    //  grad_params rows are left untouched)
+    if (grad_img && (!nlm_wsum || !out)) return AISP_ERR_NULL;
     int e = aisp_pointwise_bwd(img, grad_out, params, ops, B, H, W, clip, grad_params, grad_img, scratch,
                                scratch_bytes, stream);
     if (e) return e;
     e = aisp_sharpen_bwd(img, grad_out, params, ops, B, H, W, grad_params, grad_img, gy_scratch, scratch,
                          scratch_bytes, stream);
     if (e) return e;
-    if (nlm_dout_dh)
-        e = aisp_nlm_bwd(grad_out, nlm_dout_dh, ops, B, H, W, grad_params, nullptr, scratch, scratch_bytes, stream);
+    if (nlm_dout_dh) e = aisp_nlm_bwd(grad_out, nlm_dout_dh, ops, B, H, W, grad_params, scratch, scratch_bytes, stream);
+    if (e) return e;
+    if (grad_img) e = aisp_nlm_bwd_img(img, out, nlm_wsum, grad_out, params, ops, B, H, W, grad_img, stream);
     return e;
 }
 

@@ -43,7 +43,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <bool WITH_GRAD>
 __global__ void __launch_bounds__(kThreads, 2)
 nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __restrict__ dout_dh,
-           const float* __restrict__ params, const int32_t* __restrict__ ops, int H, int W) {
+           float* __restrict__ wsum_out, const float* __restrict__ params, const int32_t* __restrict__ ops, int H,
+           int W) {
     __shared__ float sY[kNlmSmH][kNlmSmW];
     __shared__ float sC[3][kNlmSmH][kNlmSmW];
     const int b = blockIdx.z;
@@ -145,6 +146,7 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
         const int gy = y0 + r0 + i;
         if (gy >= H) continue;
         const float iw = 1.0f / wsum[i];
+        if (wsum_out) wsum_out[(size_t)b * plane + (size_t)gy * W + gx] = wsum[i];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float y = ac[c][i] * iw;
@@ -183,12 +185,133 @@ cudaError_t launch_finalize(const float* partial, int nrows, const float* params
 int pointwise_rows(int H, int W);
 
 cudaError_t launch_nlm_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,
-                           float* dout_dh, cudaStream_t st) {
+                           float* dout_dh, float* wsum, cudaStream_t st) {
     dim3 grid((W + kNlmTileW - 1) / kNlmTileW, (H + kNlmTileH - 1) / kNlmTileH, B);
     if (dout_dh)
-        nlm_kernel<true><<<grid, kThreads, 0, st>>>(img, out, dout_dh, params, ops, H, W);
+        nlm_kernel<true><<<grid, kThreads, 0, st>>>(img, out, dout_dh, wsum, params, ops, H, W);
     else
-        nlm_kernel<false><<<grid, kThreads, 0, st>>>(img, out, nullptr, params, ops, H, W);
+        nlm_kernel<false><<<grid, kThreads, 0, st>>>(img, out, nullptr, wsum, params, ops, H, W);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// d L / d img of NLM.  Rare path (the reference's training never needs it: train.py:255), written
+// for correctness and determinism, not speed: gather-only, no atomics.
+//
+// With U_c = gy_c / W, S = sum_c U_c y_c (gy = upstream gradient, W = sum of weights, y = output):
+//   direct term      gxc_c(r) += sum_s w_s(r) * U_c(r+s)                (w_s(r-s) == w_-s(r))
+//   through weights  a_s(p)   = sum_c U_c(p) x_c(p+s) - S(p)            d L / d w_s(p)
+//                    delta_s(p) = -(w_s(p) / (2 hh d_s(p))) * (a_s(p) + a_-s(p+s)),   0 where box == 0
+//                    gY(r)   += 2 (Y(r) - Y(r+s)) * box5x5[delta_s](r)
+//   and gx = (gxc + luma * gY) * [0 <= x <= 1]   (the leading clip of DenoiseFilter.process).
+// The (s, -s) pair shares one squared difference, which is why both directions fold into delta_s.
+// CTA <-> (sample, 16x16 tile); per shift: phase A fills delta on tile+2, phase B box-sums it.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGiT = 16, kGiA = kGiT + 14, kGiY = kGiT + 18, kGiD = kGiT + 4;
+
+__global__ void __launch_bounds__(kThreads)
+nlm_bwd_img_kernel(const float* __restrict__ img, const float* __restrict__ outp, const float* __restrict__ wsum,
+                   const float* __restrict__ gout, const float* __restrict__ params, const int32_t* __restrict__ ops,
+                   int H, int W, float* __restrict__ gimg) {
+    __shared__ float sY[kGiY][kGiY + 1];
+    __shared__ float sX[3][kGiA][kGiA + 1];
+    __shared__ float sU[3][kGiA][kGiA + 1];
+    __shared__ float sS[kGiA][kGiA + 1];
+    __shared__ float sD[kGiD][kGiD + 1];
+    __shared__ float sW[kGiD][kGiD + 1];
+    const int b = blockIdx.z;
+    if (ops[b] != AISP_OP_NLM) return;
+    const int x0 = blockIdx.x * kGiT, y0 = blockIdx.y * kGiT;
+    const size_t plane = (size_t)H * W;
+    const float* src = img + (size_t)b * 3 * plane;
+    const float* yo = outp + (size_t)b * 3 * plane;
+    const float* go = gout + (size_t)b * 3 * plane;
+    const float* ws = wsum + (size_t)b * plane;
+
+    for (int e = threadIdx.x; e < kGiY * kGiY; e += kThreads) {
+        const int row = e / kGiY, col = e - row * kGiY;
+        const size_t off = (size_t)wrap(y0 - 9 + row, H) * W + wrap(x0 - 9 + col, W);
+        const float r = clip01(__ldg(src + off)), g = clip01(__ldg(src + plane + off)),
+                    bl = clip01(__ldg(src + 2 * plane + off));
+        sY[row][col] = (0.299f * r + 0.587f * g) + 0.114f * bl;
+    }
+    for (int e = threadIdx.x; e < kGiA * kGiA; e += kThreads) {
+        const int row = e / kGiA, col = e - row * kGiA;
+        const size_t off = (size_t)wrap(y0 - 7 + row, H) * W + wrap(x0 - 7 + col, W);
+        const float iw = 1.0f / __ldg(ws + off);
+        float ssum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float u = __ldg(go + c * plane + off) * iw;
+            sX[c][row][col] = clip01(__ldg(src + c * plane + off));
+            sU[c][row][col] = u;
+            ssum = fmaf(u, __ldg(yo + c * plane + off), ssum);
+        }
+        sS[row][col] = ssum;
+    }
+    __syncthreads();
+
+    const float h = params[(size_t)b * AISP_PSTRIDE];
+    const float hh = fmaxf(h, 0.f) + 1e-8f;
+    const float negk = -1.4426950408889634f / hh;
+    const float half_inv_hh = 0.5f / hh;
+    const int ty = threadIdx.x / kGiT, tx = threadIdx.x % kGiT;
+    float gy_acc = 0.f, gc[3] = {0.f, 0.f, 0.f};
+
+    for (int sx = -5; sx <= 5; ++sx) {
+        for (int sy = -5; sy <= 5; ++sy) {
+            for (int i = threadIdx.x; i < kGiD * kGiD; i += kThreads) {
+                const int py = i / kGiD, px = i - py * kGiD;
+                float box = 0.f;
+#pragma unroll
+                for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 5; ++kx) {
+                        const float t = sY[py + ky + 5][px + kx + 5] - sY[py + ky + 5 + sy][px + kx + 5 + sx];
+                        box = fmaf(t, t, box);
+                    }
+                const float d = sqrtf(box);
+                const float w = exp2f(d * negk);
+                const float kappa = (box > 0.f) ? w * half_inv_hh / d : 0.f;
+                const int ay = py + 5, ax = px + 5;          // p in aux coordinates
+                const int by = ay + sy, bx = ax + sx;        // p + s
+                float afwd = -sS[ay][ax], arev = -sS[by][bx];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    afwd = fmaf(sU[c][ay][ax], sX[c][by][bx], afwd);
+                    arev = fmaf(sU[c][by][bx], sX[c][ay][ax], arev);
+                }
+                sD[py][px] = -kappa * (afwd + arev);
+                sW[py][px] = w;
+            }
+            __syncthreads();
+            float gam = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) gam += sD[ty + ky][tx + kx];
+            gy_acc = fmaf(2.0f * (sY[ty + 9][tx + 9] - sY[ty + 9 + sy][tx + 9 + sx]), gam, gy_acc);
+            const float wr = sW[ty + 2][tx + 2];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gc[c] = fmaf(wr, sU[c][ty + 7 + sy][tx + 7 + sx], gc[c]);
+            __syncthreads();
+        }
+    }
+    const int gx = x0 + tx, gyy = y0 + ty;
+    if (gx >= W || gyy >= H) return;
+    const float lw[3] = {0.299f, 0.587f, 0.114f};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const size_t o = (size_t)c * plane + (size_t)gyy * W + gx;
+        gimg[(size_t)b * 3 * plane + o] = (gc[c] + lw[c] * gy_acc) * pass01(src[o]);
+    }
+}
+
+cudaError_t launch_nlm_bwd_img(const float* img, const float* out, const float* wsum, const float* gout,
+                               const float* params, const int32_t* ops, int B, int H, int W, float* gimg,
+                               cudaStream_t st) {
+    dim3 grid((W + kGiT - 1) / kGiT, (H + kGiT - 1) / kGiT, B);
+    nlm_bwd_img_kernel<<<grid, kThreads, 0, st>>>(img, out, wsum, gout, params, ops, H, W, gimg);
     return cudaGetLastError();
 }
 

@@ -65,10 +65,12 @@ class _ApplyOps(torch.autograd.Function):
         L = _lib.lib()
         st = _lib.stream_ptr(img.device)
         out = torch.empty_like(img)
-        want_pgrad = ctx.needs_input_grad[1]
-        stash = None
-        if family in (FAMILY_NLM, FAMILY_MIXED) and want_pgrad:
-            stash = torch.empty_like(img)
+        want_pgrad, want_igrad = ctx.needs_input_grad[1], ctx.needs_input_grad[0]
+        has_nlm = family in (FAMILY_NLM, FAMILY_MIXED)
+        # NLM stashes: d out/d h (parameter gradient as one dot product) and the weight sums
+        # (needed by the image-gradient kernel); rows of non-NLM samples are never touched
+        stash = torch.empty_like(img) if (has_nlm and want_pgrad) else None
+        wsum = torch.empty((B, 1, H, W), dtype=img.dtype, device=img.device) if (has_nlm and want_igrad) else None
         with torch.cuda.device(img.device):
             if family == FAMILY_POINTWISE:
                 rc = L.aisp_pointwise_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), ops.data_ptr(), None,
@@ -77,19 +79,19 @@ class _ApplyOps(torch.autograd.Function):
                 rc = L.aisp_sharpen_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), ops.data_ptr(), B, H, W, st)
             elif family == FAMILY_NLM:
                 rc = L.aisp_nlm_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), ops.data_ptr(), B, H, W,
-                                    _lib.ptr(stash), st)
+                                    _lib.ptr(stash), _lib.ptr(wsum), st)
             else:
                 rc = L.aisp_select_apply_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), ops.data_ptr(),
-                                             B, H, W, int(clip), _lib.ptr(stash), st)
+                                             B, H, W, int(clip), _lib.ptr(stash), _lib.ptr(wsum), st)
         _lib.check(rc, f"aisp {family} forward")
-        ctx.save_for_backward(img, P, ops, stash)
+        ctx.save_for_backward(img, P, ops, stash, wsum, out if wsum is not None else None)
         ctx.clip = bool(clip)
         ctx.family = family
         return out
 
     @staticmethod
     def backward(ctx, g):
-        img, P, ops, stash = ctx.saved_tensors
+        img, P, ops, stash, wsum, out = ctx.saved_tensors
         B, _, H, W = img.shape
         need_img, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (need_img or need_p):
@@ -105,11 +107,6 @@ class _ApplyOps(torch.autograd.Function):
         gy = None
         if need_img and family in (FAMILY_SHARPEN, FAMILY_MIXED):
             gy = torch.empty_like(img)
-        if need_img and family in (FAMILY_NLM, FAMILY_MIXED) and (
-                family == FAMILY_NLM or bool((ops == OP_NLM).any())):
-            raise NotImplementedError(
-                "d/d img of the NLM denoise filter is not implemented (the reference's training never asks for it: "
-                "train.py:255 makes the image a leaf); detach the image or exclude NLM samples")
         sc = _lib.scratch(B, H, W, img.device)
         with torch.cuda.device(img.device):
             if family == FAMILY_POINTWISE:
@@ -119,13 +116,16 @@ class _ApplyOps(torch.autograd.Function):
                 rc = L.aisp_sharpen_bwd(img.data_ptr(), g.data_ptr(), P.data_ptr(), ops.data_ptr(), B, H, W,
                                         gP.data_ptr(), _lib.ptr(gimg), _lib.ptr(gy), sc.data_ptr(), sc.numel(), st)
             elif family == FAMILY_NLM:
-                if stash is None:
-                    raise _lib.AispError("NLM backward needs the d out/d h stash written by the forward")
-                rc = L.aisp_nlm_bwd(g.data_ptr(), stash.data_ptr(), ops.data_ptr(), B, H, W, gP.data_ptr(), None,
-                                    sc.data_ptr(), sc.numel(), st)
+                rc = 0
+                if need_p and stash is not None:
+                    rc = L.aisp_nlm_bwd(g.data_ptr(), stash.data_ptr(), ops.data_ptr(), B, H, W, gP.data_ptr(),
+                                        sc.data_ptr(), sc.numel(), st)
+                if rc == 0 and need_img:
+                    rc = L.aisp_nlm_bwd_img(img.data_ptr(), out.data_ptr(), wsum.data_ptr(), g.data_ptr(), P.data_ptr(),
+                                            ops.data_ptr(), B, H, W, gimg.data_ptr(), st)
             else:
-                rc = L.aisp_select_apply_bwd(img.data_ptr(), g.data_ptr(), P.data_ptr(), ops.data_ptr(), B, H, W,
-                                             int(ctx.clip), None if need_img else _lib.ptr(stash), gP.data_ptr(),
+                rc = L.aisp_select_apply_bwd(img.data_ptr(), _lib.ptr(out), g.data_ptr(), P.data_ptr(), ops.data_ptr(),
+                                             B, H, W, int(ctx.clip), _lib.ptr(stash), _lib.ptr(wsum), gP.data_ptr(),
                                              _lib.ptr(gimg), _lib.ptr(gy), sc.data_ptr(), sc.numel(), st)
         _lib.check(rc, f"aisp {family} backward")
         return gimg, (gP if need_p else None), None, None, None
@@ -237,6 +237,6 @@ def run_pipeline(img: torch.Tensor, steps: Sequence[Sequence[int]], params: Sequ
                 _lib.check(L.aisp_sharpen_fwd(x.data_ptr(), nxt.data_ptr(), P1.data_ptr(), st_ops.data_ptr(), Bn, H, W,
                                               _lib.stream_ptr(dev)), "aisp_sharpen_fwd")
                 _lib.check(L.aisp_nlm_fwd(x.data_ptr(), nxt.data_ptr(), P1.data_ptr(), st_ops.data_ptr(), Bn, H, W,
-                                          None, _lib.stream_ptr(dev)), "aisp_nlm_fwd")
+                                          None, None, _lib.stream_ptr(dev)), "aisp_nlm_fwd")
         x = nxt
     return x if nphase > 0 else img.clone()

@@ -195,7 +195,7 @@ def run_b200(args):
         elif fam == AF.FAMILY_SHARPEN:
             rc = L.aisp_sharpen_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), o.data_ptr(), B, H, W, st)
         else:
-            rc = L.aisp_nlm_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), o.data_ptr(), B, H, W, stash.data_ptr(), st)
+            rc = L.aisp_nlm_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), o.data_ptr(), B, H, W, stash.data_ptr(), None, st)
         _lib.check(rc, "fwd " + names[i])
 
     def bwd(i):
@@ -208,7 +208,7 @@ def run_b200(args):
             rc = L.aisp_sharpen_bwd(img.data_ptr(), gout.data_ptr(), P.data_ptr(), o.data_ptr(), B, H, W,
                                     gP.data_ptr(), None, None, scratch.data_ptr(), scratch.numel(), st)
         else:
-            rc = L.aisp_nlm_bwd(gout.data_ptr(), stash.data_ptr(), o.data_ptr(), B, H, W, gP.data_ptr(), None,
+            rc = L.aisp_nlm_bwd(gout.data_ptr(), stash.data_ptr(), o.data_ptr(), B, H, W, gP.data_ptr(),
                                 scratch.data_ptr(), scratch.numel(), st)
         _lib.check(rc, "bwd " + names[i])
 

@@ -133,32 +133,42 @@ int aisp_sharpen_bwd(const float* img, const float* grad_out, const float* param
  *   dout_dh  [B,3,H,W] or NULL.  When given, the kernel also writes d out / d h per pixel and
  *            channel (clamp mask folded in), the closed form of SURVEY.md §8a row A11, so that the
  *            backward w.r.t. h is a single dot product instead of a second 121-shift pass.
+ *   wsum     [B,H,W] or NULL.  When given, the per-pixel sum of weights is stored; it is the one
+ *            extra input aisp_nlm_bwd_img needs.
  * Samples whose op is not NLM are skipped.
  */
 int aisp_nlm_fwd(const float* img, float* out, const float* params, const int32_t* ops,
-                 int B, int H, int W, float* dout_dh, void* stream);
+                 int B, int H, int W, float* dout_dh, float* wsum, void* stream);
+
+/* Backward of NLM w.r.t. h:  grad_params[b,0] = sum_{c,y,x} grad_out * dout_dh. */
+int aisp_nlm_bwd(const float* grad_out, const float* dout_dh, const int32_t* ops, int B, int H, int W,
+                 float* grad_params, void* scratch, size_t scratch_bytes, void* stream);
 
 /*
- * Backward of NLM w.r.t. h:  grad_params[b,0] = sum_{c,y,x} grad_out * dout_dh.
- * grad_img is not implemented for NLM (not needed by training, train.py:255): passing a non-NULL
- * grad_img returns AISP_ERR_UNSUPPORTED.
+ * Backward of NLM w.r.t. the image (autograd through isp/denoise.py:93-119 and the leading clip
+ * of isp/filters.py:583): both the shifted-RGB gather and the dependence of every weight on the
+ * luma patches.  Needs the forward's `out` and `wsum`.  Gather-only and deterministic; written for
+ * correctness, not speed -- the reference's training never requests it (train.py:255).
  */
-int aisp_nlm_bwd(const float* grad_out, const float* dout_dh, const int32_t* ops, int B, int H, int W,
-                 float* grad_params, float* grad_img, void* scratch, size_t scratch_bytes, void* stream);
+int aisp_nlm_bwd_img(const float* img, const float* out, const float* wsum, const float* grad_out,
+                     const float* params, const int32_t* ops, int B, int H, int W, float* grad_img,
+                     void* stream);
 
 /*
  * Apply the selected filter of each sample: the B200 form of agent.py:103-116,154, where the
  * reference runs all 10 filters on the whole batch, stacks [B,10,3,H,W] and keeps one of ten.
  * Issues the three family kernels back to back on `stream` (no host sync; graph-capturable);
  * every sample is processed by exactly one of them.  clip as in aisp_pointwise_fwd.
+ * nlm_dout_dh / nlm_wsum: stashes for the NLM samples (see aisp_nlm_fwd), NULL if not needed.
  */
 int aisp_select_apply_fwd(const float* img, float* out, const float* params, const int32_t* ops,
-                          int B, int H, int W, int clip, float* nlm_dout_dh, void* stream);
+                          int B, int H, int W, int clip, float* nlm_dout_dh, float* nlm_wsum, void* stream);
 
-int aisp_select_apply_bwd(const float* img, const float* grad_out, const float* params, const int32_t* ops,
-                          int B, int H, int W, int clip, const float* nlm_dout_dh, float* grad_params,
-                          float* grad_img, float* gy_scratch, void* scratch, size_t scratch_bytes,
-                          void* stream);
+/* Backward of the above.  `out` and `nlm_wsum` are only read when grad_img != NULL. */
+int aisp_select_apply_bwd(const float* img, const float* out, const float* grad_out, const float* params,
+                          const int32_t* ops, int B, int H, int W, int clip, const float* nlm_dout_dh,
+                          const float* nlm_wsum, float* grad_params, float* grad_img, float* gy_scratch,
+                          void* scratch, size_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus
 }

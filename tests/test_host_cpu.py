@@ -32,14 +32,14 @@ def header_symbols():
 def test_library_exports_every_declared_symbol(lib):
     from adaptiveisp_b200 import _lib
     syms = header_symbols()
-    assert len(syms) == 12
+    assert len(syms) == 13
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/aisp_b200.h but not exported"
     assert set(syms) == set(_lib.SIGNATURES), "ctypes binding and header disagree"
 
 
 def test_library_metadata_calls(lib):
-    assert lib.aisp_version() == 1
+    assert lib.aisp_version() == 2
     for op in range(13):
         assert lib.aisp_op_num_params(op) == O.OP_NPARAMS[op]
     assert lib.aisp_op_num_params(99) == -1
@@ -54,7 +54,8 @@ def test_library_metadata_calls(lib):
     assert lib.aisp_pointwise_fwd(p, p + 4, p, p, None, 1, 8, 8, 9, 1, None) == -2
     assert lib.aisp_pointwise_fwd(p, p, p, p, None, 1, 2, 2, 1, 1, None) == -4       # in-place refused
     assert lib.aisp_pointwise_bwd(p, p, p, p, 1, 2, 2, 1, p, None, p, 4, None) == -3  # scratch too small
-    assert lib.aisp_nlm_bwd(p, p, p, 1, 2, 2, p, p, p, 1 << 20, None) == -4           # NLM d/dimg unsupported
+    assert lib.aisp_nlm_bwd(p, p, p, 1, 2, 2, p, p, 4, None) == -3                     # scratch too small
+    assert lib.aisp_nlm_bwd_img(p, p, None, p, p, p, 1, 2, 2, p, None) == -1          # wsum stash is required
 
 
 def test_op_codes_shared_between_header_oracle_and_host():
