@@ -467,7 +467,7 @@ __device__ __forceinline__ void stage_consts(const float* __restrict__ params, c
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 4)
 pw_fwd_kernel(const float* __restrict__ img, float* __restrict__ out, const float* __restrict__ params,
               const int32_t* __restrict__ ops, const int32_t* __restrict__ seq_len, int N, int S, int clip_each) {
     static_assert(AISP_MAX_STEPS <= kWarps, "one warp per step stages the constants");
@@ -493,7 +493,7 @@ pw_fwd_kernel(const float* __restrict__ img, float* __restrict__ out, const floa
         if (!is_pointwise(sop[k])) { len = k; break; }
 
     constexpr int GROUPS = kPwChunkPx / (kThreads * VEC);
-    constexpr int G = (VEC == 4) ? 4 : 8;  // groups handled together (16 or 8 px per thread per round)
+    constexpr int G = (VEC == 4) ? 2 : 8;  // 8 px per thread per round, 4 CTAs/SM: TLP hides the load->compute->store phases
     constexpr int NPX = G * VEC;
     const size_t base = (size_t)b * 3 * (size_t)N;
     const float* pr = img + base;
@@ -552,7 +552,7 @@ __device__ __forceinline__ void pw_bwd_body(const float* __restrict__ pr, const 
                                             float* red, float* dst) {
     constexpr int NACC = PwBwd<OP>::NACC;
     constexpr int GROUPS = kPwChunkPx / (kThreads * VEC);
-    constexpr int G = (VEC == 4) ? 2 : 8;  // 8 px per thread per round: 12 LDG.128 in flight
+    constexpr int G = (VEC == 4) ? 1 : 4;  // 4 px per thread per round (6 LDG.128 in flight), 3 CTAs/SM
     float acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
@@ -591,7 +591,7 @@ __device__ __forceinline__ void pw_bwd_body(const float* __restrict__ pr, const 
 }
 
 template <int VEC, bool GIMG>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 pw_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, const float* __restrict__ params,
               const int32_t* __restrict__ ops, int N, int clip, float* __restrict__ gimg,
               float* __restrict__ partial) {
