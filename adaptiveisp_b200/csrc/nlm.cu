@@ -40,8 +40,36 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// Blackwell packed fp32 (PTX ISA 8.6, sm_100+): one instruction, two IEEE fp32 results.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo2(f32x2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo;
+}
+__device__ __forceinline__ float hi2(f32x2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return hi;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 template <bool WITH_GRAD>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __restrict__ dout_dh,
            float* __restrict__ wsum_out, const float* __restrict__ params, const int32_t* __restrict__ ops, int H,
            int W) {
@@ -78,13 +106,16 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
 #pragma unroll
     for (int j = 0; j < kNlmRows + 4; ++j) yo[j] = sY[r0 + j + 5][lane + 5];
 
-    float wsum[kNlmRows], ac[3][kNlmRows], wd[kNlmRows], bc[3][kNlmRows];
+    float ac[3][kNlmRows], bc[3][kNlmRows];
+    f32x2 wsum2[kNlmRows / 2], wd2[kNlmRows / 2];
+    const f32x2 negk2 = pack2(negk, negk);
 #pragma unroll
     for (int i = 0; i < kNlmRows; ++i) {
-        wsum[i] = 0.f; wd[i] = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) { ac[c][i] = 0.f; bc[c][i] = 0.f; }
     }
+#pragma unroll
+    for (int i = 0; i < kNlmRows / 2; ++i) { wsum2[i] = pack2(0.f, 0.f); wd2[i] = pack2(0.f, 0.f); }
 
     // source offsets run +5 .. -5 so that terms are accumulated in the reference's order
     // (x_shift outer, y_shift inner, shifted(p) = x(p - shift); denoise.py:106-109)
@@ -114,25 +145,42 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
             v[1] = (a12 + m34) + d[5];
             v[2] = (d[2] + m34) + a56;
             v[3] = m34 + (a56 + d[7]);
+            // Rows are handled in pairs so that the adds / multiplies that do not touch the (row-
+            // misaligned) RGB column run as Blackwell packed-fp32 instructions (FADD2 / FMUL2: two
+            // lanes of work per issue slot -- the kernel is issue-bound, not FMA-pipe-bound).
 #pragma unroll
-            for (int i = 0; i < kNlmRows; ++i) {
+            for (int i = 0; i < kNlmRows; i += 2) {
                 // 5-wide sum across lanes l .. l+4  (box centred on output column x0 + lane)
-                const float p2 = v[i] + __shfl_down_sync(0xffffffffu, v[i], 1);
-                const float p4 = p2 + __shfl_down_sync(0xffffffffu, p2, 2);
-                const float box = p4 + __shfl_down_sync(0xffffffffu, v[i], 4);
-                const float dist = sqrt_approx(box);          // box >= 0: the relu is a no-op
-                const float w = ex2_approx(dist * negk);
-                wsum[i] += w;
+                const f32x2 vv = pack2(v[i], v[i + 1]);
+                const f32x2 p2 = add2(vv, pack2(__shfl_down_sync(0xffffffffu, v[i], 1),
+                                                __shfl_down_sync(0xffffffffu, v[i + 1], 1)));
+                const f32x2 p4 = add2(p2, pack2(__shfl_down_sync(0xffffffffu, lo2(p2), 2),
+                                                __shfl_down_sync(0xffffffffu, hi2(p2), 2)));
+                const f32x2 box = add2(p4, pack2(__shfl_down_sync(0xffffffffu, v[i], 4),
+                                                 __shfl_down_sync(0xffffffffu, v[i + 1], 4)));
+                // box >= 0: the reference's relu is a no-op
+                const f32x2 dist = pack2(sqrt_approx(lo2(box)), sqrt_approx(hi2(box)));
+                const f32x2 arg = mul2(dist, negk2);
+                const float w0 = ex2_approx(lo2(arg)), w1 = ex2_approx(hi2(arg));
+                const f32x2 ww = pack2(w0, w1);
+                wsum2[i >> 1] = add2(wsum2[i >> 1], ww);
                 const int t = i + dy + 5;
-                ac[0][i] = fmaf(w, cs[0][t], ac[0][i]);
-                ac[1][i] = fmaf(w, cs[1][t], ac[1][i]);
-                ac[2][i] = fmaf(w, cs[2][t], ac[2][i]);
+                ac[0][i] = fmaf(w0, cs[0][t], ac[0][i]);
+                ac[1][i] = fmaf(w0, cs[1][t], ac[1][i]);
+                ac[2][i] = fmaf(w0, cs[2][t], ac[2][i]);
+                ac[0][i + 1] = fmaf(w1, cs[0][t + 1], ac[0][i + 1]);
+                ac[1][i + 1] = fmaf(w1, cs[1][t + 1], ac[1][i + 1]);
+                ac[2][i + 1] = fmaf(w1, cs[2][t + 1], ac[2][i + 1]);
                 if (WITH_GRAD) {
-                    const float wdi = w * dist;
-                    wd[i] += wdi;
-                    bc[0][i] = fmaf(wdi, cs[0][t], bc[0][i]);
-                    bc[1][i] = fmaf(wdi, cs[1][t], bc[1][i]);
-                    bc[2][i] = fmaf(wdi, cs[2][t], bc[2][i]);
+                    const f32x2 wdi = mul2(ww, dist);
+                    wd2[i >> 1] = add2(wd2[i >> 1], wdi);
+                    const float e0 = lo2(wdi), e1 = hi2(wdi);
+                    bc[0][i] = fmaf(e0, cs[0][t], bc[0][i]);
+                    bc[1][i] = fmaf(e0, cs[1][t], bc[1][i]);
+                    bc[2][i] = fmaf(e0, cs[2][t], bc[2][i]);
+                    bc[0][i + 1] = fmaf(e1, cs[0][t + 1], bc[0][i + 1]);
+                    bc[1][i + 1] = fmaf(e1, cs[1][t + 1], bc[1][i + 1]);
+                    bc[2][i + 1] = fmaf(e1, cs[2][t + 1], bc[2][i + 1]);
                 }
             }
         }
@@ -141,6 +189,12 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
     const int gx = x0 + lane;
     if (lane >= kNlmTileW || gx >= W) return;
     const float inv_h2 = (h > 0.f) ? 1.0f / (hh * hh) : 0.f;  // relu'(h)
+    float wsum[kNlmRows], wd[kNlmRows];
+#pragma unroll
+    for (int i = 0; i < kNlmRows / 2; ++i) {
+        wsum[2 * i] = lo2(wsum2[i]); wsum[2 * i + 1] = hi2(wsum2[i]);
+        wd[2 * i] = lo2(wd2[i]); wd[2 * i + 1] = hi2(wd2[i]);
+    }
 #pragma unroll
     for (int i = 0; i < kNlmRows; ++i) {
         const int gy = y0 + r0 + i;
