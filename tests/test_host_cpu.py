@@ -153,3 +153,23 @@ def test_reference_config_accepts_dropin_classes():
         assert mine.get_short_name() == theirs.get_short_name()
         assert {k: tuple(v.shape) for k, v in mine.state_dict().items()} == \
                {k: tuple(v.shape) for k, v in theirs.state_dict().items()}
+
+
+def test_replay_segmentation_and_reference_file_formats():
+    from adaptiveisp_b200 import replay
+    from adaptiveisp_b200.config import make_cfg
+    E, G, CCM, SHR, NLM, T = O.OP_EXPOSURE, O.OP_GAMMA, O.OP_CCM, O.OP_SHARPEN, O.OP_NLM, O.OP_TONE
+    assert replay.segment([E, G, CCM]) == [[0, 1, 2]]
+    assert replay.segment([E, SHR, G, T, NLM]) == [[0], [1], [2, 3], [4]]
+    assert replay.segment([NLM, NLM]) == [[0], [1]]
+    assert replay.segment([]) == []
+    assert [len(s) for s in replay.segment([E] * 11)] == [8, 3]            # AISP_MAX_STEPS per fused pass
+    # param_results/<img>.json as written by yolov3/val_adaptiveisp.py:301-327
+    cfg = make_cfg()
+    text = '{"pipeline": [2, 5, 0], "CCM": [1.5, -0.2, -0.3, 0.1, 1.2, -0.3, 0.0, -0.4, 1.4], ' \
+           '"T": [[[[0.6]]], [[[0.7]]], [[[0.8]]], [[[0.9]]], [[[1.0]]], [[[1.1]]], [[[1.2]]], [[[1.3]]]], "E": [0.25]}'
+    ops, plist = replay.parse_param_results(text, cfg.filters)
+    assert ops == [O.OP_CCM, O.OP_TONE, O.OP_EXPOSURE]
+    assert [p.numel() for p in plist] == [9, 8, 1] and float(plist[1][3]) == pytest.approx(0.9)
+    header, rec = replay.parse_records("E,G,CCM,Shr,NLM,T,Ct,S+,BW,W\nimg1.png,2,5,0,-1,-1\nimg2.png,4,4,4,4,4\n")
+    assert header[4] == "NLM" and rec == {"img1.png": [2, 5, 0], "img2.png": [4, 4, 4, 4, 4]}
