@@ -357,6 +357,11 @@ def run_b200(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks.summary([(tw0, tw1)] + win),
         }
+        if world == 1 and not args.no_extras:
+            try:
+                line["extras"] = extras(dev, L, peak)
+            except Exception as e:  # the extras never invalidate the headline line
+                line["extras"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu:
             mps, dt, cores = cpu_step(8, 4)
             line["cpu_baseline"] = {"value": mps, "unit": "MP/s", "cores": cores, "kind": "port",
@@ -367,6 +372,113 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def extras(dev, L, peak):
+    """Secondary configurations of BASELINE.json (not the headline): a few timed iterations each."""
+    import numpy as np
+    from adaptiveisp_b200 import _lib, functional as AF, replay
+    from adaptiveisp_b200.synthetic import lod_batch
+    from adaptiveisp_b200.config import make_cfg
+
+    def timed(fn, iters=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / iters
+
+    out = {}
+    st = torch.cuda.current_stream(dev).cuda_stream
+    cfg = make_cfg()
+    rng = np.random.RandomState(11)
+    # (a) Agent semantics (agent.py:103-116,154): ONE selected filter per sample, heterogeneous launch
+    B = B_PER_GPU
+    img = lod_batch(B, H, W, seed=1240, device=dev)
+    g = torch.randn_like(img)
+    ops_h = rng.randint(0, 10, size=B)
+    P = torch.zeros((B, 24), device=dev)
+    for b in range(B):
+        f = cfg.filters[int(ops_h[b])](cfg)
+        raw = torch.randn((1, f.get_num_filter_parameters())) * 0.3
+        if f.OP == AF.OP_CCM:
+            raw = raw * 0.3 + torch.eye(3).reshape(1, 9) * 0.6
+        P[b, :f.get_num_filter_parameters()] = f.filter_param_regressor(raw).reshape(-1).to(dev)
+    ops_d = torch.tensor([cfg.filters[int(i)].OP for i in ops_h], dtype=torch.int32, device=dev)
+    o, stash, gP = torch.empty_like(img), torch.empty_like(img), torch.zeros((B, 24), device=dev)
+    sc = _lib.scratch(B, H, W, dev)
+
+    def agent_step():
+        _lib.check(L.aisp_select_apply_fwd(img.data_ptr(), o.data_ptr(), P.data_ptr(), ops_d.data_ptr(), B, H, W, 1,
+                                           stash.data_ptr(), None, st), "select fwd")
+        _lib.check(L.aisp_select_apply_bwd(img.data_ptr(), None, g.data_ptr(), P.data_ptr(), ops_d.data_ptr(), B, H, W,
+                                           1, stash.data_ptr(), None, gP.data_ptr(), None, None, sc.data_ptr(),
+                                           sc.numel(), st), "select bwd")
+    ms = timed(agent_step, 10)
+    out["agent_select_one_of_ten"] = {"batch": B, "ms_fwd_bwd": round(ms, 4), "MP_s": round(B * H * W / 1e6 / (ms / 1e3), 1),
+                                      "nlm_samples": int((ops_h == 4).sum()), "launches": 8}
+    del img, g, o, stash
+    # (b) configs[3]: 8 x 3840x2160, desaturation / NLM / USM separately (forward + backward)
+    B4, H4, W4 = 8, 2160, 3840
+    img = lod_batch(B4, H4, W4, seed=1237, letterbox=False, device=dev)
+    g = torch.randn_like(img)
+    o, stash = torch.empty_like(img), torch.empty_like(img)
+    gP = torch.zeros((B4, 24), device=dev)
+    sc = _lib.scratch(B4, H4, W4, dev)
+    npx = B4 * H4 * W4
+    res = {}
+    for name, op, pvals in (("BW", AF.OP_WNB, [0.4]), ("NLM", AF.OP_NLM, [0.3]), ("USM", AF.OP_USM, [1.0, 1.2])):
+        Pk = torch.zeros((B4, 24), device=dev)
+        Pk[:, :len(pvals)] = torch.tensor(pvals, device=dev)
+        od = torch.full((B4,), op, dtype=torch.int32, device=dev)
+        if op == AF.OP_WNB:
+            fw = lambda: L.aisp_pointwise_fwd(img.data_ptr(), o.data_ptr(), Pk.data_ptr(), od.data_ptr(), None, B4, H4, W4, 1, 1, st)
+            bw = lambda: L.aisp_pointwise_bwd(img.data_ptr(), g.data_ptr(), Pk.data_ptr(), od.data_ptr(), B4, H4, W4, 1,
+                                              gP.data_ptr(), None, sc.data_ptr(), sc.numel(), st)
+        elif op == AF.OP_USM:
+            fw = lambda: L.aisp_sharpen_fwd(img.data_ptr(), o.data_ptr(), Pk.data_ptr(), od.data_ptr(), B4, H4, W4, st)
+            bw = lambda: L.aisp_sharpen_bwd(img.data_ptr(), g.data_ptr(), Pk.data_ptr(), od.data_ptr(), B4, H4, W4,
+                                            gP.data_ptr(), None, None, sc.data_ptr(), sc.numel(), st)
+        else:
+            fw = lambda: L.aisp_nlm_fwd(img.data_ptr(), o.data_ptr(), Pk.data_ptr(), od.data_ptr(), B4, H4, W4,
+                                        stash.data_ptr(), None, st)
+            bw = lambda: L.aisp_nlm_bwd(g.data_ptr(), stash.data_ptr(), od.data_ptr(), B4, H4, W4, gP.data_ptr(),
+                                        sc.data_ptr(), sc.numel(), st)
+        tf, tb = timed(fw, 3), timed(bw, 3)
+        res[name] = {"fwd_ms": round(tf, 3), "bwd_ms": round(tb, 3), "fwd_GBs": round(24 * npx / 1e9 / (tf / 1e3), 1),
+                     "bwd_GBs": round(24 * npx / 1e9 / (tb / 1e3), 1)}
+    tot = sum(v["fwd_ms"] + v["bwd_ms"] for v in res.values())
+    res["chain_MP_s_fwd_bwd"] = round(3 * npx / 1e6 / (tot / 1e3), 1)
+    out["config4_4k_b8"] = res
+    del img, g, o, stash
+    # (c) configs[4]: 256 x 512x512, per-sample sequences of 1..5 filters, planned replay (forward)
+    B5 = 256
+    runtime = np.array(cfg.filters_runtime, dtype=np.float64)
+    prob = (1.0 / runtime) / (1.0 / runtime).sum()
+    steps = [[int(cfg.filters[int(v)].OP) for v in rng.choice(10, size=rng.randint(1, 6), p=prob)] for _ in range(B5)]
+    params = []
+    for seq in steps:
+        row = []
+        for op in seq:
+            n = AF.NUM_PARAMS[op]
+            v = torch.rand(n) * 0.5 + 0.4
+            if op == AF.OP_CCM:
+                v = torch.eye(3).reshape(-1) + 0.1 * torch.rand(9)
+            row.append(v)
+        params.append(row)
+    plan = replay.plan_pipeline(steps, params, dev)
+    img = lod_batch(B5, H, W, seed=1238, device=dev)
+    ms = timed(lambda: replay.execute_plan(img, plan, True), 3)
+    napp = sum(len(s) for s in steps)
+    out["config5_hetero_b256"] = {"ms_fwd": round(ms, 3), "filter_applications": napp, "phases": len(plan.phases),
+                                  "launches": plan.launches, "MP_s_fwd": round(napp * H * W / 1e6 / (ms / 1e3), 1),
+                                  "nlm_applications": sum(s.count(AF.OP_NLM) for s in steps)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -374,6 +486,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary configurations")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

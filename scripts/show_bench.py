@@ -10,3 +10,5 @@ for line in sys.stdin:
         print("  ", k)
     if "cpu_baseline" in d:
         print("cpu", d["cpu_baseline"])
+    if "extras" in d:
+        print("extras", json.dumps(d["extras"], indent=1))
