@@ -69,7 +69,7 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 }
 
 template <bool WITH_GRAD>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, WITH_GRAD ? 3 : 4)
 nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __restrict__ dout_dh,
            float* __restrict__ wsum_out, const float* __restrict__ params, const int32_t* __restrict__ ops, int H,
            int W) {

@@ -1,0 +1,33 @@
+"""Touch every kernel once at small, ragged sizes (used under compute-sanitizer)."""
+import sys
+import torch
+sys.path.insert(0, ".")
+from adaptiveisp_b200 import functional as AF, replay
+from adaptiveisp_b200.synthetic import lod_batch
+
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+for (B, H, W) in [(3, 37, 53), (2, 48, 64), (1, 9, 130)]:
+    img = (torch.rand((B, 3, H, W), device=dev) * 1.2 - 0.1)
+    g = torch.randn_like(img)
+    for op in range(13):
+        n = AF.NUM_PARAMS[op]
+        p = torch.rand((B, n), device=dev) * 0.6 + 0.5
+        if op == AF.OP_CCM:
+            p = torch.eye(3, device=dev).reshape(1, 9).repeat(B, 1) + 0.1 * torch.rand((B, 9), device=dev)
+        for clip in (True, False):
+            x = img.clone().requires_grad_(True)
+            pp = p.clone().requires_grad_(True)
+            y = AF.apply_filter(x, pp, op, clip)
+            (y * g).sum().backward()
+    ops = torch.tensor([(i * 5) % 13 for i in range(B)], dtype=torch.int32, device=dev)
+    P = torch.rand((B, 24), device=dev) * 0.5 + 0.6
+    x = img.clone().requires_grad_(True)
+    Pq = P.clone().requires_grad_(True)
+    y = AF.apply_ops(x, Pq, ops, True)
+    (y * g).sum().backward()
+    steps = [[0, 1, 3, 9, 4][: 1 + b % 5] for b in range(B)]
+    params = [[torch.rand(AF.NUM_PARAMS[o]) * 0.5 + 0.5 for o in s] for s in steps]
+    out = replay.execute_plan(img, replay.plan_pipeline(steps, params, dev), True)
+torch.cuda.synchronize()
+print("sanity_all_kernels: ok", float(out.mean()))
