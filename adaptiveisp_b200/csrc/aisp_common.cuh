@@ -68,7 +68,13 @@ struct Pack<1> {
 };
 
 // torch.clip semantics: NaN stays NaN (fminf/fmaxf would swallow it)
-__device__ __forceinline__ float clip01(float y) { return y < 0.f ? 0.f : (y > 1.f ? 1.f : y); }
+__device__ __forceinline__ float clip01(float y) {
+    // two NaN-propagating FMNMX instead of two compare+select pairs
+    float r;
+    asm("min.NaN.f32 %0, %1, 0f3F800000;" : "=f"(r) : "f"(y));
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(r));
+    return r;
+}
 // clamp backward: gradient passes iff lo <= y <= hi, inclusive (NaN -> 0)
 __device__ __forceinline__ float pass01(float y) { return (y >= 0.f && y <= 1.f) ? 1.f : 0.f; }
 

@@ -50,11 +50,13 @@ __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
 __device__ __forceinline__ float lo2(f32x2 v) {
     float lo, hi;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    (void)hi;
     return lo;
 }
 __device__ __forceinline__ float hi2(f32x2 v) {
     float lo, hi;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    (void)lo;
     return hi;
 }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {

@@ -76,7 +76,7 @@ __device__ __forceinline__ void load_consts(const float* __restrict__ params, in
 
 // blur (and optionally d blur / d sigma) of a 4x2 block for one plane.
 // (bx, by): block origin inside the tile.  blur[r][i], dblur[r][i].
-template <bool USM, bool WITH_D>
+template <bool USM, bool WITH_D, bool FRAME>
 __device__ __forceinline__ void block_blur(const float (*sm)[kSmW], int bx, int by, const float* sc, int gx0, int gy0,
                                            int H, int W, float (&xc)[2][4], float (&blur)[2][4],
                                            float (&dblur)[2][4]) {
@@ -125,10 +125,12 @@ __device__ __forceinline__ void block_blur(const float (*sm)[kSmW], int bx, int 
             for (int i = 0; i < 4; ++i) {
                 const float x = ctr[r + 1][i];
                 const float ring = (hs[r][i] + hs[r + 2][i]) + (hs[r + 1][i] - x);
-                const int gx = gx0 + i, gy = gy0 + r;
-                const bool border = (gx == 0) || (gy == 0) || (gx == W - 1) || (gy == H - 1);
                 xc[r][i] = x;
-                blur[r][i] = border ? x : fmaf(a, ring, bc * x);
+                blur[r][i] = fmaf(a, ring, bc * x);
+                if (FRAME) {  // only tiles that touch the image frame pay for the pass-through test
+                    const int gx = gx0 + i, gy = gy0 + r;
+                    if ((gx == 0) || (gy == 0) || (gx == W - 1) || (gy == H - 1)) blur[r][i] = x;
+                }
                 if (WITH_D) dblur[r][i] = 0.f;
             }
     }
@@ -160,6 +162,7 @@ sharpen_kernel(const float* __restrict__ img, const float* __restrict__ gout, fl
     const int gx0 = x0 + bx, gy0 = y0 + by;
     const bool vec_ok = vec && (gx0 + 3 < W);  // vec: W % 4 == 0 and 16B-aligned global pointers
     float acc[2] = {0.f, 0.f};
+    const bool frame_tile = (x0 == 0) || (y0 == 0) || (x0 + kShTileW >= W) || (y0 + kShTileH >= H);  // CTA-uniform
     // upstream gradient of this thread's 3 x 2 x 4 outputs: requested before the tile has landed
     float gpre[3][2][4];
     if (BWD) {
@@ -187,9 +190,11 @@ sharpen_kernel(const float* __restrict__ img, const float* __restrict__ gout, fl
     for (int ch = 0; ch < 3; ++ch) {
         float xc[2][4], blur[2][4], dblur[2][4];
         if (op == AISP_OP_USM)
-            block_blur<true, BWD>(sm[ch], bx, by, sc, gx0, gy0, H, W, xc, blur, dblur);
+            block_blur<true, BWD, false>(sm[ch], bx, by, sc, gx0, gy0, H, W, xc, blur, dblur);
+        else if (frame_tile)
+            block_blur<false, BWD, true>(sm[ch], bx, by, sc, gx0, gy0, H, W, xc, blur, dblur);
         else
-            block_blur<false, BWD>(sm[ch], bx, by, sc, gx0, gy0, H, W, xc, blur, dblur);
+            block_blur<false, BWD, false>(sm[ch], bx, by, sc, gx0, gy0, H, W, xc, blur, dblur);
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int gy = gy0 + r;
