@@ -142,7 +142,7 @@ __device__ __forceinline__ float sharpen_value(int op, float x, float blur, floa
 }
 
 template <bool BWD, bool WRITE_GY>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, BWD ? 3 : 4)
 sharpen_kernel(const float* __restrict__ img, const float* __restrict__ gout, float* __restrict__ out,
                const float* __restrict__ params, const int32_t* __restrict__ ops, int H, int W, int vec,
                float* __restrict__ partial) {
