@@ -136,7 +136,7 @@ def agent_golden(ref):
             m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
             m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
     for k, v in agent.state_dict().items():
-        out["sd." + k] = v.numpy()
+        out["sd." + k] = v.numpy().copy()   # copy: .numpy() aliases the live buffers, which train-mode forwards mutate
     B = 4
     x = cases.edge_image(B, 32, 32, seed=7, in_range=True)
     z = torch.rand((B, cfg.z_dim), generator=g)
@@ -146,7 +146,10 @@ def agent_golden(ref):
     gout = cases.grad_out(x.shape, seed=7)
     out["x"], out["z"], out["states"], out["gout"] = x.numpy(), z.numpy(), states.numpy(), gout.numpy()
 
+    sd0 = {k: v.clone() for k, v in agent.state_dict().items()}
+
     def run(tag, train, forced):
+        agent.load_state_dict(sd0)      # train-mode forwards move the BatchNorm running statistics
         agent.train(train)
         agent.zero_grad(set_to_none=True)
         (xo, ns, sur, pen), dbg, _ = agent((x, z, states), 0.25, None, forced)
@@ -168,6 +171,25 @@ def agent_golden(ref):
     run("eval", False, None)
     for f in range(len(cfg.filters)):
         run(f"forced{f}", False, f)
+
+    # 5-step rollouts as in yolov3/val_adaptiveisp.py:288-309 (eval mode: argmax selection) and with
+    # sampled selection (train mode, as the replay-memory loop of train.py:234-381 carries images on)
+    for tag, train in (("rollout_eval", False), ("rollout_train", True)):
+        agent.load_state_dict(sd0)
+        agent.train(train)
+        noises = torch.rand((cfg.test_steps, B, cfg.z_dim), generator=g)
+        st = torch.zeros((B, cfg.num_state_dim))
+        cur = x
+        out[f"{tag}.noises"] = noises.numpy()
+        with torch.no_grad():
+            for i in range(cfg.test_steps):
+                (cur, st, _, _), dbg, _ = agent((cur, noises[i], st), 1.0, None, None)
+                out[f"{tag}.sel{i}"] = dbg["selected_filter"].numpy()
+                out[f"{tag}.x{i}"] = cur.numpy()
+                out[f"{tag}.states{i}"] = st.numpy()
+                if st[0][1] > 0:
+                    break
+        out[f"{tag}.steps_run"] = np.array([i + 1])
     return out
 
 
