@@ -16,6 +16,7 @@ cudaError_t launch_nlm_bwd_img(const float*, const float*, const float*, const f
                                int, int, float*, cudaStream_t);
 cudaError_t launch_nlm_bwd(const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*,
                            cudaStream_t);
+cudaError_t launch_block_mean(const float*, float*, int, int, int, int, int, cudaStream_t);
 int pointwise_rows(int H, int W);
 int sharpen_rows(int H, int W);
 }  // namespace aisp
@@ -122,6 +123,13 @@ int aisp_nlm_bwd_img(const float* img, const float* out, const float* wsum, cons
     if (!img || !out || !wsum || !grad_out || !params || !ops || !grad_img) return AISP_ERR_NULL;
     if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
     return (int)launch_nlm_bwd_img(img, out, wsum, grad_out, params, ops, B, H, W, grad_img, (cudaStream_t)stream);
+}
+
+int aisp_block_mean(const float* img, float* down, int B, int H, int W, int out_h, int out_w, void* stream) {
+    if (!img || !down) return AISP_ERR_NULL;
+    if (!shape_ok(B, H, W) || out_h <= 0 || out_w <= 0 || (long long)B * 3 > 65535) return AISP_ERR_SHAPE;
+    if (H % out_h != 0 || W % out_w != 0) return AISP_ERR_UNSUPPORTED;  // adaptive pooling with uneven windows
+    return (int)launch_block_mean(img, down, B, H, W, out_h, out_w, (cudaStream_t)stream);
 }
 
 int aisp_select_apply_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,

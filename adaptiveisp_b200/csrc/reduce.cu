@@ -1,0 +1,54 @@
+// Block-mean down-sampling of an image batch in one streaming pass.
+//
+// The consumers of a retouched batch in the reference each re-read the full-resolution image:
+// AdaptiveAvgPool2d(64,64) in Agent.forward (agent.py:97) and in Value.forward (value.py:63), the
+// per-image mean of the truncation / pool-refill tests (train.py:288-290,374) and the NaN/Inf guard
+// (train.py:374).  All of them are functions of the 64x64 block-mean image (the mean of equal-size
+// block means is the image mean; a block mean is non-finite iff the block holds a non-finite
+// value), so ONE pass producing that image replaces five or six passes over HBM.
+//
+// Thread <-> one output element; a warp covers 32 adjacent output columns, i.e. 32*bw contiguous
+// input floats per row (128-bit loads when bw % 4 == 0).  Read-only, 12 B/px.
+#include "aisp_common.cuh"
+
+namespace aisp {
+
+__global__ void __launch_bounds__(kThreads)
+block_mean_kernel(const float* __restrict__ img, float* __restrict__ down, int H, int W, int oh, int ow, int bh,
+                  int bw, int vec) {
+    const int plane = blockIdx.z;                                   // b * 3 + c
+    const int ox = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int oy = blockIdx.y * kWarps + (threadIdx.x >> 5);
+    if (ox >= ow || oy >= oh) return;
+    const float* src = img + (size_t)plane * H * W + (size_t)oy * bh * W + (size_t)ox * bw;
+    float acc = 0.f;
+    if (vec) {
+        for (int r = 0; r < bh; ++r) {
+            const float* row = src + (size_t)r * W;
+            float s = 0.f;
+            for (int c = 0; c < bw; c += 4) {
+                const float4 v = ldg_stream4(row + c);
+                s += (v.x + v.y) + (v.z + v.w);
+            }
+            acc += s;
+        }
+    } else {
+        for (int r = 0; r < bh; ++r) {
+            const float* row = src + (size_t)r * W;
+            float s = 0.f;
+            for (int c = 0; c < bw; ++c) s += __ldg(row + c);
+            acc += s;
+        }
+    }
+    down[((size_t)plane * oh + oy) * ow + ox] = acc / (float)(bh * bw);
+}
+
+cudaError_t launch_block_mean(const float* img, float* down, int B, int H, int W, int oh, int ow, cudaStream_t st) {
+    const int bh = H / oh, bw = W / ow;
+    const int vec = ((bw & 3) == 0) && ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(img) & 15u) == 0);
+    dim3 grid((ow + 31) / 32, (oh + kWarps - 1) / kWarps, B * 3);
+    block_mean_kernel<<<grid, kThreads, 0, st>>>(img, down, H, W, oh, ow, bh, bw, vec);
+    return cudaGetLastError();
+}
+
+}  // namespace aisp

@@ -150,6 +150,26 @@ def apply_filter(img: torch.Tensor, param: torch.Tensor, op: int, clip: bool) ->
 
 
 @torch.no_grad()
+def block_mean(img: torch.Tensor, out_hw=(64, 64)) -> torch.Tensor:
+    """``nn.AdaptiveAvgPool2d(out_hw)`` for evenly dividing sizes, in one streaming read (no autograd:
+    the reference only pools images that carry no gradient, agent.py:97 / train.py:255)."""
+    _lib.require_image(img, "img")
+    B, _, H, W = img.shape
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+    down = torch.empty((B, 3, oh, ow), dtype=torch.float32, device=img.device)
+    with torch.cuda.device(img.device):
+        rc = _lib.lib().aisp_block_mean(img.data_ptr(), down.data_ptr(), B, H, W, oh, ow, _lib.stream_ptr(img.device))
+    _lib.check(rc, "aisp_block_mean")
+    return down
+
+
+def image_stats(down: torch.Tensor):
+    """Per-image mean and finiteness from the block-mean image (train.py:288-290,374): the mean of
+    equal-size block means is the image mean; a block mean is finite iff its whole block is."""
+    return down.mean(dim=(1, 2, 3)), torch.isfinite(down).flatten(1).all(dim=1)
+
+
+@torch.no_grad()
 def chain_forward(img: torch.Tensor, P: torch.Tensor, ops: torch.Tensor, seq_len: Optional[torch.Tensor] = None,
                   clip_each: bool = True) -> torch.Tensor:
     """Per-sample sequences of per-pixel filters fused into ONE pass over HBM (forward only).

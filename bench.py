@@ -420,6 +420,11 @@ def extras(dev, L, peak):
     ms = timed(agent_step, 10)
     out["agent_select_one_of_ten"] = {"batch": B, "ms_fwd_bwd": round(ms, 4), "MP_s": round(B * H * W / 1e6 / (ms / 1e3), 1),
                                       "nlm_samples": int((ops_h == 4).sum()), "launches": 8}
+    # (a2) SURVEY §8(f)-1: the 64x64 block-mean image in one pass vs nn.AdaptiveAvgPool2d
+    pool = torch.nn.AdaptiveAvgPool2d((64, 64))
+    t_k, t_t = timed(lambda: AF.block_mean(img, (64, 64)), 10), timed(lambda: pool(img), 10)
+    out["block_mean_64x64"] = {"ms": round(t_k, 4), "GBs": round(12 * B * H * W / 1e9 / (t_k / 1e3), 1),
+                               "torch_adaptive_avg_pool_ms": round(t_t, 4)}
     del img, g, o, stash
     # (b) configs[3]: 8 x 3840x2160, desaturation / NLM / USM separately (forward + backward)
     B4, H4, W4 = 8, 2160, 3840

@@ -155,6 +155,15 @@ int aisp_nlm_bwd_img(const float* img, const float* out, const float* wsum, cons
                      void* stream);
 
 /*
+ * Block-mean down-sampling [B,3,H,W] -> [B,3,out_h,out_w] in one read-only pass; requires
+ * H % out_h == 0 and W % out_w == 0 (then identical to nn.AdaptiveAvgPool2d((out_h,out_w)),
+ * agent.py:97 / value.py:63; otherwise AISP_ERR_UNSUPPORTED).  The per-image mean and the NaN/Inf
+ * guard of train.py:288-290,374 are functions of this small image, so the five or six
+ * full-resolution reads the reference spends on them collapse into this one.
+ */
+int aisp_block_mean(const float* img, float* down, int B, int H, int W, int out_h, int out_w, void* stream);
+
+/*
  * Apply the selected filter of each sample: the B200 form of agent.py:103-116,154, where the
  * reference runs all 10 filters on the whole batch, stacks [B,10,3,H,W] and keeps one of ten.
  * Issues the three family kernels back to back on `stream` (no host sync; graph-capturable);
