@@ -22,7 +22,25 @@ block_mean_kernel(const float* __restrict__ img, float* __restrict__ down, int H
     if (ox >= ow || oy >= oh) return;
     const float* src = img + (size_t)plane * H * W + (size_t)oy * bh * W + (size_t)ox * bw;
     float acc = 0.f;
-    if (vec) {
+    if (vec && bw == 8) {  // the 512 -> 64 case: two 128-bit loads per row, four rows in flight
+        int r = 0;
+        for (; r + 4 <= bh; r += 4) {
+            float4 v[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[2 * k] = ldg_stream4(src + (size_t)(r + k) * W);
+                v[2 * k + 1] = ldg_stream4(src + (size_t)(r + k) * W + 4);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                acc += ((v[2 * k].x + v[2 * k].y) + (v[2 * k].z + v[2 * k].w)) +
+                       ((v[2 * k + 1].x + v[2 * k + 1].y) + (v[2 * k + 1].z + v[2 * k + 1].w));
+        }
+        for (; r < bh; ++r) {
+            const float4 a = ldg_stream4(src + (size_t)r * W), b = ldg_stream4(src + (size_t)r * W + 4);
+            acc += ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+        }
+    } else if (vec) {
         for (int r = 0; r < bh; ++r) {
             const float* row = src + (size_t)r * W;
             float s = 0.f;

@@ -40,6 +40,32 @@ METRIC = "isp_chain_megapixels_per_sec_fwd_bwd"
 ALGO_BYTES_FWD, ALGO_BYTES_BWD = 24, 24  # B/px, SURVEY.md §8(d): fwd r12+w12, bwd (param grads) r12+r12
 
 
+# per-launch DRAM traffic measured by ncu (--set full) at this workload, profiles/r01_ncu_summary.txt
+NCU_TRAFFIC_BYTES = {"NLM": 550.5e6, "pw_fwd": 352.9e6, "pw_bwd": 410.6e6, "sharpen_fwd": 355.2e6, "sharpen_bwd": 407.2e6}
+# SASS instructions per (pixel, shift) of nlm_kernel<grad>'s main loop (993 per 44, cuobjdump) and lane use
+NLM_INSTR_PER_PXSHIFT, NLM_LANE_EFF = 993.0 / 44.0, 28.0 / 32.0
+
+
+def nlm_issue_bound(fwd_ms, npx, sm_mhz):
+    """NLM against the bound that actually limits it: warp-instruction issue (4 per clock per SM)."""
+    thread_instr = npx * 121 * NLM_INSTR_PER_PXSHIFT / NLM_LANE_EFF
+    ideal_ms = thread_instr / (148 * 128 * sm_mhz * 1e6) * 1e3
+    return {"ideal_ms_at_full_issue_rate": round(ideal_ms, 3), "measured_ms": round(fwd_ms, 3),
+            "frac": round(ideal_ms / fwd_ms, 3), "sm_mhz": sm_mhz,
+            "model": "B*H*W*121 shifts * 22.6 SASS instr / (28/32 lanes) / (148 SMs * 128 thread-instr/clk)"}
+
+
+def clk_mhz(clocks):
+    vals = []
+    for _, line in clocks.samples:
+        try:
+            vals.append(float(line.split(",")[0]))
+        except ValueError:
+            pass
+    vals.sort()
+    return vals[len(vals) // 2] if vals else 1965.0
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -343,9 +369,16 @@ def run_b200(args):
                        "parallelism": f"dp{world} (batch-sharded replicas, no collective in the ISP path)"},
             "roofline": {"bound": "hbm", "kernel": ("nlm_kernel<grad>" if dom["filter"] == "NLM" else dom["filter"]) +
                          (" fwd" if dom_fwd else " bwd"), "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                         "note": "NLM is FP32/MUFU-bound by construction (121 patch distances, sqrt and exp per "
-                                 "pixel), see DESIGN.md; HBM fractions of the HBM-bound kernels are in 'kernels'"},
+                         "frac": ach / peak, "peak_source": peak_src,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
+                         # ncu --set full capture (profiles/r01_ncu_summary.txt); NLM also writes its d/dh stash
+                         "traffic": NCU_TRAFFIC_BYTES.get("NLM" if dom["filter"] == "NLM" else
+                                                          ("pw_fwd" if dom_fwd else "pw_bwd")),
+                         "note": "NLM is SM-issue/FP32/MUFU-bound by construction (121 patch distances, sqrt and exp "
+                                 "per pixel), not HBM-bound: see 'issue_bound' and DESIGN.md 4.3; the HBM fractions "
+                                 "of the HBM-bound kernels are in 'kernels' / 'hbm_frac_excl_nlm'",
+                         "issue_bound": nlm_issue_bound(kern["NLM"][0], npx, (clocks.samples and clk_mhz(clocks)) or 1965.0)
+                         if "NLM" in kern else None},
             "hbm_frac_step": step_bytes / 1e9 / (ms_max / args.steps / 1e3) / peak,
             "hbm_frac_excl_nlm": pw_bytes / 1e9 / (pw_ms / 1e3) / peak,
             "kernels": klist,
