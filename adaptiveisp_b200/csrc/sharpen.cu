@@ -4,18 +4,32 @@
 //   SHARPEN_V2  y = clip(x + (x - blur3(x))*f)      isp/sharpen.py:145-182
 //   USM         y = clip(x + (x - G_sigma*x)*a)     isp/sharpen.py:84-102   (5x5, reflect padding)
 //
-// CTA <-> (sample, 128x16 tile); the tile plus a 2-px halo of all three planes is staged in shared
-// memory once with 128-bit row copies (border rule applied while staging), each thread produces a
-// 4x2 block per plane from registers (separable 5-tap passes for USM), so HBM sees ~24 B/px fwd and
-// ~24 B/px bwd; halo rows/columns re-read by neighbouring CTAs are L2 hits.
+// CTA <-> (sample, 128x16 tile).  The tile plus a 2-px halo of all three planes is staged in shared
+// memory by ONE TMA bulk-tensor copy (cp.async.bulk.tensor.3d over a [B*3, H, W] tensor map, box
+// 3 x 20 x 136 starting at column x0-4 -- the innermost TMA coordinate must be 16-byte aligned
+// (measured: x0-2 raises an illegal-instruction fault) --, completion on an mbarrier): a single thread issues it, no warp spends instructions on
+// addresses, and out-of-bounds halo elements arrive as zeros.  That is exactly right for the 3x3
+// filters (frame pixels pass through and interior pixels never read outside the image) and for USM
+// tiles that do not touch the image frame; USM frame tiles (reflect padding) and images whose rows
+// are not 16-byte multiples take the cp.async path, which applies the reflect rule per element.
+// Each thread then produces a 4x2 block per plane from registers (separable 5-tap passes for USM),
+// so HBM sees ~24 B/px forward and ~24 B/px backward; halo re-reads by neighbouring CTAs hit L2.
+#include <cstring>
+#include <cstring>
+
+#include <cuda.h>  // CUtensorMap and enums only; cuTensorMapEncodeTiled is resolved through the runtime
+
 #include "aisp_common.cuh"
 
 namespace aisp {
 
 constexpr int kHalo = 2;
-constexpr int kSmW = kShTileW + 8;             // 4 floats of left pad keep the interior 16B aligned
-constexpr int kSmH = kShTileH + 2 * kHalo;
-constexpr int kColOff = 4;                     // smem column of tile column 0
+constexpr int kSmH = kShTileH + 2 * kHalo;           // 20 rows
+constexpr int kCpW = kShTileW + 8;                   // 136 columns per staged row, tile column 0 at smem column 4:
+constexpr int kColOff = 4;                           //   a TMA box must start on a 16-byte boundary of the row
+constexpr int kTmaW = kCpW;                          //   (x0 - 4), which also keeps cp.async 16-byte aligned
+constexpr int kSmFloats = 3 * kSmH * kCpW;
+constexpr unsigned kTmaBytes = 3u * kSmH * kTmaW * sizeof(float);
 
 __device__ __forceinline__ int reflect_clamp(int i, int n) {
     if (i < 0) i = -i;
@@ -23,9 +37,37 @@ __device__ __forceinline__ int reflect_clamp(int i, int n) {
     return min(max(i, 0), n - 1);
 }
 
-// Ampere-style async copies (LDGSTS): global -> shared without a register round trip, so a CTA's
-// whole tile is in flight at once and the staging of one CTA overlaps the arithmetic of its
-// neighbours on the SM.
+// ---- TMA + mbarrier primitives (PTX; SASS: UTMALDG / SYNCS) ----------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "AISP_MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra AISP_MBAR_DONE;\n\t"
+        "bra AISP_MBAR_WAIT;\n"
+        "AISP_MBAR_DONE:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, int c0, int c1, int c2,
+                                            unsigned long long* bar) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem);
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(d), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(b)
+        : "memory");
+}
+
+// ---- cp.async (LDGSTS) fallback staging --------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
@@ -38,11 +80,10 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// stage tile + halo of one sample (3 planes) into shared memory: a warp copies whole rows, one
-// 16-byte async copy per lane for the 128 interior columns, and lanes 0..3 fetch the four halo
-// columns; the border rule (reflect, clamped) is applied on the way in.
-__device__ __forceinline__ void stage_tile(const float* __restrict__ img, float (*sm)[kSmH][kSmW], int H, int W,
-                                           int x0, int y0, bool vec) {
+// a warp copies whole rows: one 16-byte async copy per lane for the 128 interior columns, lanes
+// 0..3 fetch the four halo columns; the border rule (reflect, clamped) is applied on the way in.
+__device__ __forceinline__ void stage_tile_cp(const float* __restrict__ img, float* sm, int H, int W, int x0, int y0,
+                                              bool vec) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gx = x0 + 4 * lane;
     const bool own_vec = vec && (gx + 3 < W);
@@ -51,14 +92,14 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ img, float 
     for (int rr = warp; rr < 3 * kSmH; rr += kWarps) {
         const int ch = rr / kSmH, row = rr - ch * kSmH;
         const float* src = img + ((size_t)ch * H + reflect_clamp(y0 - kHalo + row, H)) * W;
-        float* dst = &sm[ch][row][kColOff + 4 * lane];
+        float* dst = sm + (ch * kSmH + row) * kCpW + 4 + 4 * lane;
         if (own_vec) {
             cp_async16(dst, src + gx);
         } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) cp_async4(dst + i, src + reflect_clamp(gx + i, W));
         }
-        if (lane < 4) cp_async4(&sm[ch][row][kColOff + hc], src + hx);
+        if (lane < 4) cp_async4(sm + (ch * kSmH + row) * kCpW + 4 + hc, src + hx);
     }
 }
 
@@ -75,11 +116,10 @@ __device__ __forceinline__ void load_consts(const float* __restrict__ params, in
 }
 
 // blur (and optionally d blur / d sigma) of a 4x2 block for one plane.
-// (bx, by): block origin inside the tile.  blur[r][i], dblur[r][i].
-template <bool USM, bool WITH_D, bool FRAME>
-__device__ __forceinline__ void block_blur(const float (*sm)[kSmW], int bx, int by, const float* sc, int gx0, int gy0,
-                                           int H, int W, float (&xc)[2][4], float (&blur)[2][4],
-                                           float (&dblur)[2][4]) {
+//   sm: plane base, SW: row stride, COFF: smem column of tile column 0; (bx, by): block origin in the tile.
+template <bool USM, bool WITH_D, bool FRAME, int SW, int COFF>
+__device__ __forceinline__ void block_blur(const float* sm, int bx, int by, const float* sc, int gx0, int gy0, int H,
+                                           int W, float (&xc)[2][4], float (&blur)[2][4], float (&dblur)[2][4]) {
     if (USM) {
         float hk[6][4], hd[6][4];
         const float k0 = sc[0], k1 = sc[1], k2 = sc[2];
@@ -88,7 +128,7 @@ __device__ __forceinline__ void block_blur(const float (*sm)[kSmW], int bx, int 
         for (int r = 0; r < 6; ++r) {
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = sm[by + r][bx + kColOff - 2 + i];
+            for (int i = 0; i < 8; ++i) v[i] = sm[(by + r) * SW + bx + COFF - 2 + i];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float e2 = v[i] + v[i + 4], e1 = v[i + 1] + v[i + 3], e0 = v[i + 2];
@@ -115,7 +155,7 @@ __device__ __forceinline__ void block_blur(const float (*sm)[kSmW], int bx, int 
         for (int r = 0; r < 4; ++r) {
             float v[6];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) v[i] = sm[by + 1 + r][bx + kColOff - 1 + i];
+            for (int i = 0; i < 6; ++i) v[i] = sm[(by + 1 + r) * SW + bx + COFF - 1 + i];
 #pragma unroll
             for (int i = 0; i < 4; ++i) { hs[r][i] = (v[i] + v[i + 1]) + v[i + 2]; ctr[r][i] = v[i + 1]; }
         }
@@ -143,10 +183,11 @@ __device__ __forceinline__ float sharpen_value(int op, float x, float blur, floa
 
 template <bool BWD, bool WRITE_GY>
 __global__ void __launch_bounds__(kThreads, BWD ? 3 : 4)
-sharpen_kernel(const float* __restrict__ img, const float* __restrict__ gout, float* __restrict__ out,
-               const float* __restrict__ params, const int32_t* __restrict__ ops, int H, int W, int vec,
-               float* __restrict__ partial) {
-    __shared__ __align__(16) float sm[3][kSmH][kSmW];
+sharpen_kernel(const __grid_constant__ CUtensorMap tmap, int tma_ok, const float* __restrict__ img,
+               const float* __restrict__ gout, float* __restrict__ out, const float* __restrict__ params,
+               const int32_t* __restrict__ ops, int H, int W, int vec, float* __restrict__ partial) {
+    __shared__ __align__(128) float sm[kSmFloats];
+    __shared__ __align__(8) unsigned long long bar;
     __shared__ float sc[kConst];
     __shared__ float red[kWarps * AISP_ACC_STRIDE];
     const int b = blockIdx.z;
@@ -154,7 +195,19 @@ sharpen_kernel(const float* __restrict__ img, const float* __restrict__ gout, fl
     if (!is_sharpen(op)) return;
     const int x0 = blockIdx.x * kShTileW, y0 = blockIdx.y * kShTileH;
     const size_t base = (size_t)b * 3 * H * W;
-    stage_tile(img + base, sm, H, W, x0, y0, vec != 0);
+    const bool frame_tile = (x0 == 0) || (y0 == 0) || (x0 + kShTileW >= W) || (y0 + kShTileH >= H);  // CTA-uniform
+    // zero-filled out-of-bounds halos are only wrong for reflect padding at the frame
+    const bool use_tma = tma_ok && !(op == AISP_OP_USM && frame_tile);
+    if (use_tma) {
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, kTmaBytes);
+            tma_load_3d(sm, &tmap, x0 - kColOff, y0 - kHalo, b * 3, &bar);
+        }
+    } else {
+        stage_tile_cp(img + base, sm, H, W, x0, y0, vec != 0);
+    }
     load_consts(params, b, op, sc);
 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -162,7 +215,6 @@ sharpen_kernel(const float* __restrict__ img, const float* __restrict__ gout, fl
     const int gx0 = x0 + bx, gy0 = y0 + by;
     const bool vec_ok = vec && (gx0 + 3 < W);  // vec: W % 4 == 0 and 16B-aligned global pointers
     float acc[2] = {0.f, 0.f};
-    const bool frame_tile = (x0 == 0) || (y0 == 0) || (x0 + kShTileW >= W) || (y0 + kShTileH >= H);  // CTA-uniform
     // upstream gradient of this thread's 3 x 2 x 4 outputs: requested before the tile has landed
     float gpre[3][2][4];
     if (BWD) {
@@ -182,19 +234,24 @@ sharpen_kernel(const float* __restrict__ img, const float* __restrict__ gout, fl
                 }
             }
     }
-    cp_async_wait_all();
+    if (use_tma) {
+        mbar_wait(&bar, 0);
+    } else {
+        cp_async_wait_all();
+    }
     __syncthreads();
     const float f = (op == AISP_OP_USM) ? sc[10] : sc[0];
 
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         float xc[2][4], blur[2][4], dblur[2][4];
+        const float* pl = sm + ch * kSmH * kCpW;
         if (op == AISP_OP_USM)
-            block_blur<true, BWD, false>(sm[ch], bx, by, sc, gx0, gy0, H, W, xc, blur, dblur);
+            block_blur<true, BWD, false, kCpW, kColOff>(pl, bx, by, sc, gx0, gy0, H, W, xc, blur, dblur);
         else if (frame_tile)
-            block_blur<false, BWD, true>(sm[ch], bx, by, sc, gx0, gy0, H, W, xc, blur, dblur);
+            block_blur<false, BWD, true, kCpW, kColOff>(pl, bx, by, sc, gx0, gy0, H, W, xc, blur, dblur);
         else
-            block_blur<false, BWD, false>(sm[ch], bx, by, sc, gx0, gy0, H, W, xc, blur, dblur);
+            block_blur<false, BWD, false, kCpW, kColOff>(pl, bx, by, sc, gx0, gy0, H, W, xc, blur, dblur);
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int gy = gy0 + r;
@@ -338,6 +395,9 @@ sharpen_adjoint_kernel(const float* __restrict__ gy, float* __restrict__ gimg, c
 // ---------------------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------------
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int sharpen_rows(int H, int W) {
@@ -347,11 +407,47 @@ int sharpen_rows(int H, int W) {
 cudaError_t launch_finalize(const float* partial, int nrows, const float* params, const int32_t* ops, int family,
                             int B, float* grad_params, cudaStream_t st);
 
+// [B*3, H, W] fp32 tensor map with a 3 x 20 x 136 box.  Returns false when TMA cannot describe the
+// image (rows not a multiple of 16 bytes, unaligned base, too many planes) -> cp.async path.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static bool make_tile_map(CUtensorMap* map, const float* img, int B, int H, int W) {
+    memset(map, 0, sizeof(*map));
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || (W & 3) != 0 || !al16(img) || W < 4) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * 3};
+    const cuuint64_t gstr[2] = {(cuuint64_t)W * sizeof(float), (cuuint64_t)W * H * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)kTmaW, (cuuint32_t)kSmH, 3};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(img), gdim, gstr, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 cudaError_t launch_sharpen_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H,
                                int W, cudaStream_t st) {
     dim3 grid((W + kShTileW - 1) / kShTileW, (H + kShTileH - 1) / kShTileH, B);
     const int vec = ((W & 3) == 0) && al16(img) && al16(out);
-    sharpen_kernel<false, false><<<grid, kThreads, 0, st>>>(img, nullptr, out, params, ops, H, W, vec, nullptr);
+    CUtensorMap map;
+    const int tma_ok = make_tile_map(&map, img, B, H, W) ? 1 : 0;
+    sharpen_kernel<false, false><<<grid, kThreads, 0, st>>>(map, tma_ok, img, nullptr, out, params, ops, H, W, vec,
+                                                            nullptr);
     return cudaGetLastError();
 }
 
@@ -360,10 +456,14 @@ cudaError_t launch_sharpen_bwd(const float* img, const float* gout, const float*
                                cudaStream_t st) {
     dim3 grid((W + kShTileW - 1) / kShTileW, (H + kShTileH - 1) / kShTileH, B);
     const int vec = ((W & 3) == 0) && al16(img) && al16(gout) && (!grad_img || al16(gy_scratch));
+    CUtensorMap map;
+    const int tma_ok = make_tile_map(&map, img, B, H, W) ? 1 : 0;
     if (grad_img)
-        sharpen_kernel<true, true><<<grid, kThreads, 0, st>>>(img, gout, gy_scratch, params, ops, H, W, vec, partial);
+        sharpen_kernel<true, true><<<grid, kThreads, 0, st>>>(map, tma_ok, img, gout, gy_scratch, params, ops, H, W, vec,
+                                                              partial);
     else
-        sharpen_kernel<true, false><<<grid, kThreads, 0, st>>>(img, gout, nullptr, params, ops, H, W, vec, partial);
+        sharpen_kernel<true, false><<<grid, kThreads, 0, st>>>(map, tma_ok, img, gout, nullptr, params, ops, H, W, vec,
+                                                               partial);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     e = launch_finalize(partial, sharpen_rows(H, W), params, ops, FAMILY_SHARPEN, B, grad_params, st);
