@@ -67,6 +67,32 @@ struct Pack<1> {
     __device__ __forceinline__ void store(float* p) const { stg_stream1(p, v[0]); }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): every kernel here is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and starts with griddepcontrol.wait, so its
+// launch/scheduling latency overlaps the tail of the previous kernel on the stream; the wait
+// returns only when the previous grid has completed and flushed, so ordering is unchanged.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // torch.clip semantics: NaN stays NaN (fminf/fmaxf would swallow it)
 __device__ __forceinline__ float clip01(float y) {
     // two NaN-propagating FMNMX instead of two compare+select pairs

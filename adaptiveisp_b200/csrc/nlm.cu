@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(kThreads, WITH_GRAD ? 3 : 4)
 nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __restrict__ dout_dh,
            float* __restrict__ wsum_out, const float* __restrict__ params, const int32_t* __restrict__ ops, int H,
            int W) {
+    pdl_prologue();
     __shared__ float sY[kNlmSmH][kNlmSmW];
     __shared__ float sC[3][kNlmSmH][kNlmSmW];
     const int b = blockIdx.z;
@@ -217,6 +218,7 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
 __global__ void __launch_bounds__(kThreads)
 nlm_dot_kernel(const float* __restrict__ gout, const float* __restrict__ stash, const int32_t* __restrict__ ops,
                long long n /* 3*H*W */, float* __restrict__ partial) {
+    pdl_prologue();
     __shared__ float red[kWarps * AISP_ACC_STRIDE];
     const int b = blockIdx.y;
     if (ops[b] != AISP_OP_NLM) return;
@@ -244,9 +246,9 @@ cudaError_t launch_nlm_fwd(const float* img, float* out, const float* params, co
                            float* dout_dh, float* wsum, cudaStream_t st) {
     dim3 grid((W + kNlmTileW - 1) / kNlmTileW, (H + kNlmTileH - 1) / kNlmTileH, B);
     if (dout_dh)
-        nlm_kernel<true><<<grid, kThreads, 0, st>>>(img, out, dout_dh, wsum, params, ops, H, W);
+        launch_pdl(nlm_kernel<true>, grid, kThreads, st, img, out, dout_dh, wsum, params, ops, H, W);
     else
-        nlm_kernel<false><<<grid, kThreads, 0, st>>>(img, out, nullptr, wsum, params, ops, H, W);
+        launch_pdl(nlm_kernel<false>, grid, kThreads, st, img, out, nullptr, wsum, params, ops, H, W);
     return cudaGetLastError();
 }
 
@@ -269,6 +271,7 @@ __global__ void __launch_bounds__(kThreads)
 nlm_bwd_img_kernel(const float* __restrict__ img, const float* __restrict__ outp, const float* __restrict__ wsum,
                    const float* __restrict__ gout, const float* __restrict__ params, const int32_t* __restrict__ ops,
                    int H, int W, float* __restrict__ gimg) {
+    pdl_prologue();
     __shared__ float sY[kGiY][kGiY + 1];
     __shared__ float sX[3][kGiA][kGiA + 1];
     __shared__ float sU[3][kGiA][kGiA + 1];
@@ -367,7 +370,7 @@ cudaError_t launch_nlm_bwd_img(const float* img, const float* out, const float* 
                                const float* params, const int32_t* ops, int B, int H, int W, float* gimg,
                                cudaStream_t st) {
     dim3 grid((W + kGiT - 1) / kGiT, (H + kGiT - 1) / kGiT, B);
-    nlm_bwd_img_kernel<<<grid, kThreads, 0, st>>>(img, out, wsum, gout, params, ops, H, W, gimg);
+    launch_pdl(nlm_bwd_img_kernel, grid, kThreads, st, img, out, wsum, gout, params, ops, H, W, gimg);
     return cudaGetLastError();
 }
 
@@ -376,7 +379,7 @@ cudaError_t launch_nlm_bwd(const float* gout, const float* stash, const float* p
     (void)params_unused;
     const int rows = pointwise_rows(H, W);
     dim3 grid(rows, B);
-    nlm_dot_kernel<<<grid, kThreads, 0, st>>>(gout, stash, ops, 3LL * H * W, partial);
+    launch_pdl(nlm_dot_kernel, grid, kThreads, st, gout, stash, ops, 3LL * H * W, partial);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // finalize reads params only to derive constants; NLM needs none, so grad_params doubles as a

@@ -470,6 +470,7 @@ template <int VEC>
 __global__ void __launch_bounds__(kThreads, 4)
 pw_fwd_kernel(const float* __restrict__ img, float* __restrict__ out, const float* __restrict__ params,
               const int32_t* __restrict__ ops, const int32_t* __restrict__ seq_len, int N, int S, int clip_each) {
+    pdl_prologue();
     static_assert(AISP_MAX_STEPS <= kWarps, "one warp per step stages the constants");
     __shared__ float raw[AISP_MAX_STEPS][kConst];
     __shared__ float sc[AISP_MAX_STEPS][kConst];
@@ -595,6 +596,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 pw_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, const float* __restrict__ params,
               const int32_t* __restrict__ ops, int N, int clip, float* __restrict__ gimg,
               float* __restrict__ partial) {
+    pdl_prologue();
     __shared__ float raw[1][kConst];
     __shared__ float sc[1][kConst];
     __shared__ int sop[1];
@@ -637,6 +639,7 @@ pw_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, con
 __global__ void __launch_bounds__(kThreads)
 finalize_kernel(const float* __restrict__ partial, int nrows, const float* __restrict__ params,
                 const int32_t* __restrict__ ops, int family, float* __restrict__ grad_params) {
+    pdl_prologue();
     __shared__ double part[kWarps][AISP_ACC_STRIDE];
     __shared__ double tot[AISP_ACC_STRIDE];
     __shared__ float raw[kConst];
@@ -681,9 +684,9 @@ cudaError_t launch_pointwise_fwd(const float* img, float* out, const float* para
     dim3 grid((unsigned)((N + kPwChunkPx - 1) / kPwChunkPx), (unsigned)B);
     const bool vec = (N % 4 == 0) && aligned16(img) && aligned16(out);
     if (vec)
-        pw_fwd_kernel<4><<<grid, kThreads, 0, st>>>(img, out, params, ops, seq_len, (int)N, S, clip_each);
+        launch_pdl(pw_fwd_kernel<4>, grid, kThreads, st, img, out, params, ops, seq_len, (int)N, S, clip_each);
     else
-        pw_fwd_kernel<1><<<grid, kThreads, 0, st>>>(img, out, params, ops, seq_len, (int)N, S, clip_each);
+        launch_pdl(pw_fwd_kernel<1>, grid, kThreads, st, img, out, params, ops, seq_len, (int)N, S, clip_each);
     return cudaGetLastError();
 }
 
@@ -691,7 +694,7 @@ int pointwise_rows(int H, int W) { return (int)(((long long)H * W + kPwChunkPx -
 
 cudaError_t launch_finalize(const float* partial, int nrows, const float* params, const int32_t* ops, int family,
                             int B, float* grad_params, cudaStream_t st) {
-    finalize_kernel<<<B, kThreads, 0, st>>>(partial, nrows, params, ops, family, grad_params);
+    launch_pdl(finalize_kernel, B, kThreads, st, partial, nrows, params, ops, family, grad_params);
     return cudaGetLastError();
 }
 
@@ -704,14 +707,14 @@ cudaError_t launch_pointwise_bwd(const float* img, const float* gout, const floa
     const bool vec = (N % 4 == 0) && aligned16(img) && aligned16(gout) && (!grad_img || aligned16(grad_img));
     if (vec) {
         if (grad_img)
-            pw_bwd_kernel<4, true><<<grid, kThreads, 0, st>>>(img, gout, params, ops, (int)N, clip, grad_img, partial);
+            launch_pdl(pw_bwd_kernel<4, true>, grid, kThreads, st, img, gout, params, ops, (int)N, clip, grad_img, partial);
         else
-            pw_bwd_kernel<4, false><<<grid, kThreads, 0, st>>>(img, gout, params, ops, (int)N, clip, nullptr, partial);
+            launch_pdl(pw_bwd_kernel<4, false>, grid, kThreads, st, img, gout, params, ops, (int)N, clip, nullptr, partial);
     } else {
         if (grad_img)
-            pw_bwd_kernel<1, true><<<grid, kThreads, 0, st>>>(img, gout, params, ops, (int)N, clip, grad_img, partial);
+            launch_pdl(pw_bwd_kernel<1, true>, grid, kThreads, st, img, gout, params, ops, (int)N, clip, grad_img, partial);
         else
-            pw_bwd_kernel<1, false><<<grid, kThreads, 0, st>>>(img, gout, params, ops, (int)N, clip, nullptr, partial);
+            launch_pdl(pw_bwd_kernel<1, false>, grid, kThreads, st, img, gout, params, ops, (int)N, clip, nullptr, partial);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

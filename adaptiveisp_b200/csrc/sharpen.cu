@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(kThreads, BWD ? 3 : 4)
 sharpen_kernel(const __grid_constant__ CUtensorMap tmap, int tma_ok, const float* __restrict__ img,
                const float* __restrict__ gout, float* __restrict__ out, const float* __restrict__ params,
                const int32_t* __restrict__ ops, int H, int W, int vec, float* __restrict__ partial) {
+    pdl_prologue();
     __shared__ __align__(128) float sm[kSmFloats];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ float sc[kConst];
@@ -337,6 +338,7 @@ __device__ __forceinline__ int mirrors(int q, int n, int* m) {
 __global__ void __launch_bounds__(kThreads)
 sharpen_adjoint_kernel(const float* __restrict__ gy, float* __restrict__ gimg, const float* __restrict__ params,
                        const int32_t* __restrict__ ops, int H, int W) {
+    pdl_prologue();
     __shared__ float sm[3][kAdjH + 4][kAdjW + 4];
     __shared__ float sc[kConst];
     __shared__ float wk[5][5];
@@ -446,7 +448,7 @@ cudaError_t launch_sharpen_fwd(const float* img, float* out, const float* params
     const int vec = ((W & 3) == 0) && al16(img) && al16(out);
     CUtensorMap map;
     const int tma_ok = make_tile_map(&map, img, B, H, W) ? 1 : 0;
-    sharpen_kernel<false, false><<<grid, kThreads, 0, st>>>(map, tma_ok, img, nullptr, out, params, ops, H, W, vec,
+    launch_pdl(sharpen_kernel<false, false>, grid, kThreads, st, map, tma_ok, img, nullptr, out, params, ops, H, W, vec,
                                                             nullptr);
     return cudaGetLastError();
 }
@@ -459,10 +461,10 @@ cudaError_t launch_sharpen_bwd(const float* img, const float* gout, const float*
     CUtensorMap map;
     const int tma_ok = make_tile_map(&map, img, B, H, W) ? 1 : 0;
     if (grad_img)
-        sharpen_kernel<true, true><<<grid, kThreads, 0, st>>>(map, tma_ok, img, gout, gy_scratch, params, ops, H, W, vec,
+        launch_pdl(sharpen_kernel<true, true>, grid, kThreads, st, map, tma_ok, img, gout, gy_scratch, params, ops, H, W, vec,
                                                               partial);
     else
-        sharpen_kernel<true, false><<<grid, kThreads, 0, st>>>(map, tma_ok, img, gout, nullptr, params, ops, H, W, vec,
+        launch_pdl(sharpen_kernel<true, false>, grid, kThreads, st, map, tma_ok, img, gout, nullptr, params, ops, H, W, vec,
                                                                partial);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -470,7 +472,7 @@ cudaError_t launch_sharpen_bwd(const float* img, const float* gout, const float*
     if (e != cudaSuccess) return e;
     if (grad_img) {
         dim3 g2((W + kAdjW - 1) / kAdjW, (H + kAdjH - 1) / kAdjH, B);
-        sharpen_adjoint_kernel<<<g2, kThreads, 0, st>>>(gy_scratch, grad_img, params, ops, H, W);
+        launch_pdl(sharpen_adjoint_kernel, g2, kThreads, st, gy_scratch, grad_img, params, ops, H, W);
         e = cudaGetLastError();
     }
     return e;
