@@ -168,3 +168,40 @@ class GraphedHostLoop:
         cur.wait_stream(self.s_in)
         cur.wait_stream(self.s_out)
         return n
+
+
+class GraphedStep:
+    """One CUDA graph around a device-resident step (e.g. ``Agent.forward`` + ``backward``).
+
+    On a B200 the eager Agent step is CPU-launch-bound (about 7 ms of launches for 1.5-3.5 ms of GPU
+    work, ``scripts/agent_step_timing.py``); replaying it as a graph removes that.  Shapes and the
+    set of modules must stay fixed; ``step_fn`` may call ``.backward()`` (parameter ``.grad`` tensors
+    become static: clear them with ``zero_grad(set_to_none=False)``).
+
+        g = GraphedStep(step_fn, example_inputs=(x, z, states), modules=[agent])
+        out = g(x_new, z_new, states_new)       # copies into the static inputs, replays, returns static outputs
+    """
+
+    def __init__(self, step_fn, example_inputs, modules=(), warmup: int = 2):
+        dev = example_inputs[0].device
+        for m in modules:
+            m.zero_grad(set_to_none=True)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                step_fn(*example_inputs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for m in modules:
+            m.zero_grad(set_to_none=True)
+        self.inputs = tuple(t.clone() for t in example_inputs)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = step_fn(*self.inputs)
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.inputs, inputs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.outputs
