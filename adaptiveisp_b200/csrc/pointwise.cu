@@ -592,7 +592,7 @@ __device__ __forceinline__ void pw_bwd_body(const float* __restrict__ pr, const 
 }
 
 template <int VEC, bool GIMG>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 pw_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, const float* __restrict__ params,
               const int32_t* __restrict__ ops, int N, int clip, float* __restrict__ gimg,
               float* __restrict__ partial) {
