@@ -85,20 +85,28 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
     const float* src = img + (size_t)b * 3 * plane;
 
     // stage clipped RGB and luma of the wrapped tile + halo       (isp/filters.py:583, denoise.py:11-17)
-    for (int e = threadIdx.x; e < kNlmSmH * kNlmSmW; e += kThreads) {
-        const int row = e / kNlmSmW, col = e - row * kNlmSmW;
-        const size_t off = (size_t)wrap(y0 - kNlmHalo + row, H) * W + wrap(x0 - kNlmHalo + col, W);
-        const float r = clip01(__ldg(src + off));
-        const float g = clip01(__ldg(src + plane + off));
-        const float bl = clip01(__ldg(src + 2 * plane + off));
-        sC[0][row][col] = r;
-        sC[1][row][col] = g;
-        sC[2][row][col] = bl;
-        sY[row][col] = (0.299f * r + 0.587f * g) + 0.114f * bl;
+    // a warp walks whole rows (row wrap once per row, column wrap by one conditional add when the
+    // image is wider than the tile footprint; the generic modulo only serves tiny images)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool wide = (W >= kNlmSmW) && (H >= kNlmSmH);
+    for (int row = warp; row < kNlmSmH; row += kWarps) {
+        int gy = y0 - kNlmHalo + row;
+        gy = wide ? (gy < 0 ? gy + H : (gy >= H ? gy - H : gy)) : wrap(gy, H);
+        const float* rp = src + (size_t)gy * W;
+        for (int col = lane; col < kNlmSmW; col += 32) {
+            int gx = x0 - kNlmHalo + col;
+            gx = wide ? (gx < 0 ? gx + W : (gx >= W ? gx - W : gx)) : wrap(gx, W);
+            const float r = clip01(__ldg(rp + gx));
+            const float g = clip01(__ldg(rp + plane + gx));
+            const float bl = clip01(__ldg(rp + 2 * plane + gx));
+            sC[0][row][col] = r;
+            sC[1][row][col] = g;
+            sC[2][row][col] = bl;
+            sY[row][col] = (0.299f * r + 0.587f * g) + 0.114f * bl;
+        }
     }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r0 = warp * kNlmRows;  // first output row of this thread, relative to y0
     const float h = params[(size_t)b * AISP_PSTRIDE];
     const float hh = fmaxf(h, 0.f) + 1e-8f;              // relu(h) + EPS   (denoise.py:112)
