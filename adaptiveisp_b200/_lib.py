@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(CSRC, "libaisp_b200.so")
 
 PSTRIDE = 24
 MAX_STEPS = 8
+MAX_CHAIN_BWD = 4
 ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/aisp_b200.h one to one
@@ -29,6 +30,8 @@ SIGNATURES = {
     "aisp_bwd_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "aisp_pointwise_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "aisp_pointwise_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "aisp_pointwise_chain_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t,
+                                         _P]),
     "aisp_sharpen_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "aisp_sharpen_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "aisp_nlm_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),

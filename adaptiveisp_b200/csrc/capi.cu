@@ -17,6 +17,9 @@ cudaError_t launch_nlm_bwd_img(const float*, const float*, const float*, const f
 cudaError_t launch_nlm_bwd(const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*,
                            cudaStream_t);
 cudaError_t launch_block_mean(const float*, float*, int, int, int, int, int, cudaStream_t);
+cudaError_t launch_pointwise_chain_bwd(const float*, const float*, const float*, const int32_t*, const int32_t*, int, int,
+                                       int, int, int, float*, float*, float*, cudaStream_t);
+int chain_bwd_max_steps();
 int pointwise_rows(int H, int W);
 int sharpen_rows(int H, int W);
 }  // namespace aisp
@@ -58,7 +61,8 @@ int aisp_op_num_params(int op) {
 size_t aisp_bwd_scratch_bytes(int B, int H, int W) {
     if (!shape_ok(B, H, W)) return 0;
     const int rows = pointwise_rows(H, W) > sharpen_rows(H, W) ? pointwise_rows(H, W) : sharpen_rows(H, W);
-    return (size_t)B * rows * AISP_ACC_STRIDE * sizeof(float);
+    // x AISP_MAX_CHAIN_BWD: the fused multi-step backward keeps one row per (chunk, stage)
+    return (size_t)B * rows * AISP_ACC_STRIDE * sizeof(float) * AISP_MAX_CHAIN_BWD;
 }
 
 int aisp_pointwise_fwd(const float* img, float* out, const float* params, const int32_t* ops, const int32_t* seq_len,
@@ -80,6 +84,18 @@ int aisp_pointwise_bwd(const float* img, const float* grad_out, const float* par
     if (!al4(img) || !al4(grad_out) || !al4(grad_img)) return AISP_ERR_ALIGN;
     return (int)launch_pointwise_bwd(img, grad_out, params, ops, B, H, W, clip ? 1 : 0, grad_params, grad_img,
                                      (float*)scratch, (cudaStream_t)stream);
+}
+
+int aisp_pointwise_chain_bwd(const float* img, const float* grad_out, const float* params, const int32_t* ops,
+                             const int32_t* seq_len, int B, int H, int W, int S, int clip_each, float* grad_params,
+                             float* grad_img, void* scratch, size_t scratch_bytes, void* stream) {
+    if (!img || !grad_out || !params || !ops || !grad_params || !scratch) return AISP_ERR_NULL;
+    if (!shape_ok(B, H, W) || S < 1) return AISP_ERR_SHAPE;
+    if (S > AISP_MAX_CHAIN_BWD || S > chain_bwd_max_steps()) return AISP_ERR_UNSUPPORTED;
+    if (scratch_bytes < aisp_bwd_scratch_bytes(B, H, W)) return AISP_ERR_SCRATCH;
+    if (!al4(img) || !al4(grad_out) || !al4(grad_img)) return AISP_ERR_ALIGN;
+    return (int)launch_pointwise_chain_bwd(img, grad_out, params, ops, seq_len, B, H, W, S, clip_each ? 1 : 0,
+                                           grad_params, grad_img, (float*)scratch, (cudaStream_t)stream);
 }
 
 int aisp_sharpen_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,

@@ -721,4 +721,229 @@ cudaError_t launch_pointwise_bwd(const float* img, const float* gout, const floa
     return launch_finalize(partial, rows, params, ops, FAMILY_POINTWISE, B, grad_params, st);
 }
 
+// =============================================================================================
+// Fused multi-step backward: a per-sample sequence of up to kChainMax per-pixel filters is
+// differentiated in ONE pass over HBM.  Per pixel the forward chain is recomputed in registers
+// (keeping every stage's input), then the stages are swept in reverse: each stage turns the
+// upstream gradient into its parameter-gradient partial sums and into the gradient w.r.t. its
+// input, which is the upstream gradient of the previous stage.  Traffic: image 12 + grad_out 12
+// (+12 for grad_img) bytes per pixel for the whole sequence -- the same as ONE single-step backward.
+// The 24-knot ColorFilter (27 partial sums) does not fit the 9-accumulator stage budget: its
+// gradient row is returned as NaN (the image gradient still flows through it correctly).
+// =============================================================================================
+constexpr int kChainMax = 4;
+constexpr int kChainAcc = 9;
+
+template <int NPX, bool GX>
+__device__ __forceinline__ void bwd_step(int op, const float* __restrict__ c, const float (&R)[NPX],
+                                         const float (&G)[NPX], const float (&B)[NPX], float (&gr)[NPX],
+                                         float (&gg)[NPX], float (&gb)[NPX], int clip, float* acc) {
+    switch (op) {
+#define AISP_CHAIN_CASE(OPC)                                                                         \
+    case OPC: {                                                                                      \
+        _Pragma("unroll") for (int i = 0; i < NPX; ++i)                                              \
+            PwBwd<OPC>::template px<GX>(c, R[i], G[i], B[i], gr[i], gg[i], gb[i], clip, acc);        \
+        break;                                                                                       \
+    }
+        AISP_CHAIN_CASE(AISP_OP_EXPOSURE)
+        AISP_CHAIN_CASE(AISP_OP_GAMMA)
+        AISP_CHAIN_CASE(AISP_OP_WB)
+        AISP_CHAIN_CASE(AISP_OP_CCM)
+        AISP_CHAIN_CASE(AISP_OP_TONE)
+        AISP_CHAIN_CASE(AISP_OP_CONTRAST)
+        AISP_CHAIN_CASE(AISP_OP_WNB)
+        AISP_CHAIN_CASE(AISP_OP_SATPLUS)
+#undef AISP_CHAIN_CASE
+    case AISP_OP_COLOR: {  // image gradient only; the parameter-gradient row is flagged NaN
+        float scratch[PwBwd<AISP_OP_COLOR>::NACC];
+#pragma unroll
+        for (int k = 0; k < PwBwd<AISP_OP_COLOR>::NACC; ++k) scratch[k] = 0.f;
+#pragma unroll
+        for (int i = 0; i < NPX; ++i)
+            PwBwd<AISP_OP_COLOR>::template px<GX>(c, R[i], G[i], B[i], gr[i], gg[i], gb[i], clip, scratch);
+        acc[0] = __int_as_float(0x7fc00000);
+        break;
+    }
+    default: break;
+    }
+}
+
+template <int VEC, bool GIMG>
+__global__ void __launch_bounds__(kThreads, 2)
+pw_chain_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, const float* __restrict__ params,
+                    const int32_t* __restrict__ ops, const int32_t* __restrict__ seq_len, int N, int S, int clip_each,
+                    float* __restrict__ gimg, float* __restrict__ partial) {
+    pdl_prologue();
+    __shared__ float raw[kChainMax][kConst];
+    __shared__ float sc[kChainMax][kConst];
+    __shared__ int sop[kChainMax];
+    __shared__ float red[kWarps * AISP_ACC_STRIDE];
+    const int b = blockIdx.y;
+    int len = seq_len ? min(max(seq_len[b], 0), S) : S;
+    if (len > 0 && !is_pointwise(ops[(size_t)b * S])) {
+        if (GIMG && ops[(size_t)b * S] == AISP_OP_NONE) {
+            float* q = gimg + (size_t)b * 3 * (size_t)N;
+            const int c0 = blockIdx.x * kPwChunkPx;
+            for (int pl = 0; pl < 3; ++pl)
+                for (int i = c0 + threadIdx.x; i < min(c0 + kPwChunkPx, N); i += kThreads) q[(size_t)pl * N + i] = 0.f;
+        }
+        return;
+    }
+    stage_consts(params, ops, b, S, len, raw, sc, sop);
+    for (int k = 0; k < len; ++k)
+        if (!is_pointwise(sop[k])) { len = k; break; }
+
+    constexpr int GROUPS = kPwChunkPx / (kThreads * VEC);
+    const size_t base = (size_t)b * 3 * (size_t)N;
+    const float* pr = img + base;
+    const float* pg = gout + base;
+    float* gi = GIMG ? gimg + base : nullptr;
+    const int chunk0 = blockIdx.x * kPwChunkPx;
+    float acc[kChainMax][kChainAcc];
+#pragma unroll
+    for (int k = 0; k < kChainMax; ++k)
+#pragma unroll
+        for (int j = 0; j < kChainAcc; ++j) acc[k][j] = 0.f;
+
+    for (int g0 = 0; g0 < GROUPS; ++g0) {
+        const int i = chunk0 + (g0 * kThreads + threadIdx.x) * VEC;
+        if (i >= N) break;
+        Pack<VEC> t;
+        float xs[kChainMax][3][VEC];
+        float R[VEC], G[VEC], B[VEC], gr[VEC], gg[VEC], gb[VEC];
+        t.load(pr + i);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) R[v] = t.v[v];
+        t.load(pr + N + i);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) G[v] = t.v[v];
+        t.load(pr + 2 * (size_t)N + i);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) B[v] = t.v[v];
+        t.load(pg + i);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) gr[v] = t.v[v];
+        t.load(pg + N + i);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) gg[v] = t.v[v];
+        t.load(pg + 2 * (size_t)N + i);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) gb[v] = t.v[v];
+        // forward recompute, remembering every stage's input
+#pragma unroll
+        for (int k = 0; k < kChainMax; ++k) {
+            if (k < len) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { xs[k][0][v] = R[v]; xs[k][1][v] = G[v]; xs[k][2][v] = B[v]; }
+                if (k + 1 < len) {  // the last stage's output is never needed
+                    fwd_step<VEC>(sop[k], sc[k], R, G, B);
+                    if (clip_each) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) { R[v] = clip01(R[v]); G[v] = clip01(G[v]); B[v] = clip01(B[v]); }
+                    }
+                }
+            }
+        }
+        // reverse sweep
+#pragma unroll
+        for (int k = kChainMax - 1; k >= 0; --k) {
+            if (k < len) {
+                if (k == 0 && !GIMG)
+                    bwd_step<VEC, false>(sop[k], sc[k], xs[k][0], xs[k][1], xs[k][2], gr, gg, gb, clip_each, acc[k]);
+                else
+                    bwd_step<VEC, true>(sop[k], sc[k], xs[k][0], xs[k][1], xs[k][2], gr, gg, gb, clip_each, acc[k]);
+            }
+        }
+        if (GIMG) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) t.v[v] = gr[v];
+            t.store(gi + i);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) t.v[v] = gg[v];
+            t.store(gi + N + i);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) t.v[v] = gb[v];
+            t.store(gi + 2 * (size_t)N + i);
+        }
+    }
+    // one scratch row per (sample, chunk, stage)
+#pragma unroll
+    for (int k = 0; k < kChainMax; ++k) {
+        if (k < S) {
+            __syncthreads();  // `red` is reused stage after stage
+            block_reduce_store<kChainAcc>(acc[k], red,
+                                          partial + (((size_t)b * gridDim.x + blockIdx.x) * S + k) * AISP_ACC_STRIDE);
+        }
+    }
+}
+
+// grid = (B, S): sums the rows of (sample b, stage k) in fp64 and applies the stage's chain rule
+__global__ void __launch_bounds__(kThreads)
+chain_finalize_kernel(const float* __restrict__ partial, int nchunks, int S, const float* __restrict__ params,
+                      const int32_t* __restrict__ ops, const int32_t* __restrict__ seq_len,
+                      float* __restrict__ grad_params) {
+    pdl_prologue();
+    __shared__ double part[kWarps][AISP_ACC_STRIDE];
+    __shared__ double tot[AISP_ACC_STRIDE];
+    __shared__ float raw[kConst];
+    __shared__ float c[kConst];
+    const int b = blockIdx.x, k = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* gp_row = grad_params + ((size_t)b * S + k) * AISP_PSTRIDE;
+    int len = seq_len ? min(max(seq_len[b], 0), S) : S;
+    bool live = (k < len) && is_pointwise(ops[(size_t)b * S]);
+    for (int j = 0; live && j <= k; ++j) live = is_pointwise(ops[(size_t)b * S + j]);
+    if (!live) {
+        if (threadIdx.x < AISP_PSTRIDE) gp_row[threadIdx.x] = 0.f;
+        return;
+    }
+    const int op = ops[(size_t)b * S + k];
+    double s = 0.0;
+    for (int r = warp; r < nchunks; r += kWarps)
+        s += (double)partial[(((size_t)b * nchunks + r) * S + k) * AISP_ACC_STRIDE + lane];
+    part[warp][lane] = s;
+    if (warp == 0) {
+        raw[lane] = (lane < AISP_PSTRIDE) ? params[((size_t)b * S + k) * AISP_PSTRIDE + lane] : 0.f;
+        c[lane] = 0.f;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += part[w][lane];
+        tot[lane] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        derive_consts(op, raw, c);
+        float gp[AISP_PSTRIDE];
+        finalize_grads(op, tot, c, raw, gp);
+        if (op == AISP_OP_COLOR)
+            for (int j = 0; j < AISP_PSTRIDE; ++j) gp[j] = __int_as_float(0x7fc00000);
+        for (int j = 0; j < AISP_PSTRIDE; ++j) gp_row[j] = gp[j];
+    }
+}
+
+cudaError_t launch_pointwise_chain_bwd(const float* img, const float* gout, const float* params, const int32_t* ops,
+                                       const int32_t* seq_len, int B, int H, int W, int S, int clip_each,
+                                       float* grad_params, float* grad_img, float* partial, cudaStream_t st) {
+    const long long N = (long long)H * W;
+    const int rows = pointwise_rows(H, W);
+    dim3 grid((unsigned)rows, (unsigned)B);
+    const bool vec = (N % 4 == 0) && aligned16(img) && aligned16(gout) && (!grad_img || aligned16(grad_img));
+    if (vec) {
+        if (grad_img) launch_pdl(pw_chain_bwd_kernel<4, true>, grid, kThreads, st, img, gout, params, ops, seq_len, (int)N, S, clip_each, grad_img, partial);
+        else launch_pdl(pw_chain_bwd_kernel<4, false>, grid, kThreads, st, img, gout, params, ops, seq_len, (int)N, S, clip_each, nullptr, partial);
+    } else {
+        if (grad_img) launch_pdl(pw_chain_bwd_kernel<1, true>, grid, kThreads, st, img, gout, params, ops, seq_len, (int)N, S, clip_each, grad_img, partial);
+        else launch_pdl(pw_chain_bwd_kernel<1, false>, grid, kThreads, st, img, gout, params, ops, seq_len, (int)N, S, clip_each, nullptr, partial);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    launch_pdl(chain_finalize_kernel, dim3(B, S), kThreads, st, partial, rows, S, params, ops, seq_len, grad_params);
+    return cudaGetLastError();
+}
+
+int chain_bwd_max_steps() { return kChainMax; }
+
 }  // namespace aisp

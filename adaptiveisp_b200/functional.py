@@ -149,6 +149,69 @@ def apply_filter(img: torch.Tensor, param: torch.Tensor, op: int, clip: bool) ->
     return apply_ops(img, pack_params(param, NUM_PARAMS[op]), op, clip, family_of(op))
 
 
+class _ApplyChain(torch.autograd.Function):
+    """Per-sample sequences of per-pixel filters, forward AND backward each fused into one pass."""
+
+    @staticmethod
+    def forward(ctx, img, P, ops, seq_len, clip_each: bool):
+        _lib.require_image(img, "img")
+        B, _, H, W = img.shape
+        S = ops.shape[1]
+        out = torch.empty_like(img)
+        with torch.cuda.device(img.device):
+            rc = _lib.lib().aisp_pointwise_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), ops.data_ptr(),
+                                               _lib.ptr(seq_len), B, H, W, S, int(clip_each),
+                                               _lib.stream_ptr(img.device))
+        _lib.check(rc, "aisp_pointwise_fwd")
+        ctx.save_for_backward(img, P, ops, seq_len)
+        ctx.clip_each = bool(clip_each)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        img, P, ops, seq_len = ctx.saved_tensors
+        need_img, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_img or need_p):
+            return None, None, None, None, None
+        B, _, H, W = img.shape
+        S = ops.shape[1]
+        g = g.contiguous()
+        gP = torch.empty_like(P)
+        gimg = torch.empty_like(img) if need_img else None
+        sc = _lib.scratch(B, H, W, img.device)
+        with torch.cuda.device(img.device):
+            rc = _lib.lib().aisp_pointwise_chain_bwd(img.data_ptr(), g.data_ptr(), P.data_ptr(), ops.data_ptr(),
+                                                     _lib.ptr(seq_len), B, H, W, S, int(ctx.clip_each), gP.data_ptr(),
+                                                     _lib.ptr(gimg), sc.data_ptr(), sc.numel(),
+                                                     _lib.stream_ptr(img.device))
+        _lib.check(rc, "aisp_pointwise_chain_bwd")
+        return gimg, (gP if need_p else None), None, None, None
+
+
+def apply_chain(img: torch.Tensor, P: torch.Tensor, ops: torch.Tensor, seq_len: Optional[torch.Tensor] = None,
+                clip_each: bool = True) -> torch.Tensor:
+    """Differentiable fused sequence: ``ops[b, :seq_len[b]]`` (per-pixel filters only) applied to image b
+    with parameter rows ``P[b, k]``; forward in one pass over HBM, backward in one pass.
+
+    img ``[B,3,H,W]``; P ``[B,S,PSTRIDE]`` (may require grad); ops int32 ``[B,S]`` with ``S <= MAX_CHAIN_BWD``
+    when gradients are needed.  ``clip_each`` as in :func:`chain_forward`.
+    """
+    B = img.shape[0]
+    S = ops.shape[1]
+    if P.shape != (B, S, PSTRIDE) or P.dtype != torch.float32 or not P.is_cuda:
+        raise _lib.AispError(f"P must be CUDA float32 [B,S,{PSTRIDE}]")
+    needs_grad = torch.is_grad_enabled() and (img.requires_grad or P.requires_grad)
+    if needs_grad and S > _lib.MAX_CHAIN_BWD:
+        raise _lib.AispError(f"a fused backward sequence holds at most {_lib.MAX_CHAIN_BWD} steps (got {S}); "
+                             "split the chain and chain the calls")
+    if not needs_grad and not (1 <= S <= MAX_STEPS):
+        raise _lib.AispError(f"sequence length {S} outside 1..{MAX_STEPS}")
+    ops = _ops_tensor(ops, B, img.device)
+    if seq_len is not None:
+        seq_len = _ops_tensor(seq_len, B, img.device)
+    return _ApplyChain.apply(img, P.contiguous(), ops, seq_len, clip_each)
+
+
 @torch.no_grad()
 def block_mean(img: torch.Tensor, out_hw=(64, 64)) -> torch.Tensor:
     """``nn.AdaptiveAvgPool2d(out_hw)`` for evenly dividing sizes, in one streaming read (no autograd:
@@ -205,58 +268,5 @@ def run_pipeline(img: torch.Tensor, steps: Sequence[Sequence[int]], params: Sequ
     boundary.  Samples are advanced phase by phase: phase p runs every sample's p-th fused segment in
     one heterogeneous launch (samples that already finished are carried through unchanged).
     """
-    _lib.require_image(img, "img")
-    B = img.shape[0]
-    dev = img.device
-    # split each sample's sequence into segments: runs of per-pixel ops, or a single stencil op
-    segs = []
-    for b in range(B):
-        cur, out = [], []
-        for k, op in enumerate(steps[b]):
-            if op in POINTWISE:
-                cur.append(k)
-                if len(cur) == MAX_STEPS:
-                    out.append(cur)
-                    cur = []
-            else:
-                if cur:
-                    out.append(cur)
-                    cur = []
-                out.append([k])
-        if cur:
-            out.append(cur)
-        segs.append(out)
-    nphase = max((len(s) for s in segs), default=0)
-    x = img
-    for p in range(nphase):
-        S = max(len(s[p]) if p < len(s) else 0 for s in segs)
-        ops_h = torch.zeros((B, S), dtype=torch.int32)
-        len_h = torch.zeros((B,), dtype=torch.int32)
-        P_h = torch.zeros((B, S, PSTRIDE), dtype=torch.float32)
-        for b in range(B):
-            if p >= len(segs[b]):
-                continue  # seq_len 0 == identity for the per-pixel kernel
-            for j, k in enumerate(segs[b][p]):
-                op = steps[b][k]
-                ops_h[b, j] = op
-                P_h[b, j, :NUM_PARAMS[op]] = params[b][k].detach().reshape(-1).float().cpu()
-            len_h[b] = len(segs[b][p])
-        ops_d, len_d, P_d = ops_h.to(dev), len_h.to(dev), P_h.to(dev)
-        nxt = chain_forward(x, P_d, ops_d, len_d, clip_each)      # skips samples led by a stencil op
-        first = ops_h[:, 0]
-        active = len_h > 0
-        if bool((active & torch.isin(first, torch.tensor(sorted(SHARPEN), dtype=torch.int32))).any()) or \
-                bool((active & (first == OP_NLM)).any()):
-            # stencil segments have length 1: run the two stencil families on the same buffers;
-            # inactive samples carry op -1 there (skipped) and were copied through by chain_forward
-            st_ops = torch.where(active, first, torch.full_like(first, -1)).to(dev)
-            L = _lib.lib()
-            Bn, _, H, W = x.shape
-            P1 = P_d[:, 0, :].contiguous()
-            with torch.cuda.device(dev):
-                _lib.check(L.aisp_sharpen_fwd(x.data_ptr(), nxt.data_ptr(), P1.data_ptr(), st_ops.data_ptr(), Bn, H, W,
-                                              _lib.stream_ptr(dev)), "aisp_sharpen_fwd")
-                _lib.check(L.aisp_nlm_fwd(x.data_ptr(), nxt.data_ptr(), P1.data_ptr(), st_ops.data_ptr(), Bn, H, W,
-                                          None, None, _lib.stream_ptr(dev)), "aisp_nlm_fwd")
-        x = nxt
-    return x if nphase > 0 else img.clone()
+    from . import replay   # planning + execution live there; this is the one-shot convenience form
+    return replay.execute_plan(img, replay.plan_pipeline(steps, params, img.device), clip_each)

@@ -453,6 +453,26 @@ def extras(dev, L, peak):
     ms = timed(agent_step, 10)
     out["agent_select_one_of_ten"] = {"batch": B, "ms_fwd_bwd": round(ms, 4), "MP_s": round(B * H * W / 1e6 / (ms / 1e3), 1),
                                       "nlm_samples": int((ops_h == 4).sum()), "launches": 8}
+    # (a1) a fused 4-stage per-pixel chain (BASELINE configs[0]'s E -> G -> WB -> CCM prefix) forward and
+    #      backward, each ONE pass over HBM: 4 filter applications for 48 B/px
+    S4 = 4
+    chain_ops = torch.tensor([[AF.OP_EXPOSURE, AF.OP_GAMMA, AF.OP_WB, AF.OP_CCM]] * B, dtype=torch.int32, device=dev)
+    Pc = torch.zeros((B, S4, 24), device=dev)
+    Pc[:, 0, 0] = 0.09012079
+    Pc[:, 1, 0] = 0.38566995
+    Pc[:, 2, :3] = torch.tensor([2.4052505, 1.2233436, 1.8800205], device=dev)
+    Pc[:, 3, :9] = torch.tensor([1.6, -0.4, -0.2, -0.3, 1.5, -0.2, -0.1, -0.5, 1.6], device=dev)
+    gPc = torch.zeros_like(Pc)
+    t_f = timed(lambda: _lib.check(L.aisp_pointwise_fwd(img.data_ptr(), o.data_ptr(), Pc.data_ptr(), chain_ops.data_ptr(),
+                                                       None, B, H, W, S4, 1, st), "chain fwd"), 10)
+    t_b = timed(lambda: _lib.check(L.aisp_pointwise_chain_bwd(img.data_ptr(), g.data_ptr(), Pc.data_ptr(),
+                                                             chain_ops.data_ptr(), None, B, H, W, S4, 1, gPc.data_ptr(),
+                                                             None, sc.data_ptr(), sc.numel(), st), "chain bwd"), 10)
+    out["fused_chain_E_G_WB_CCM"] = {
+        "fwd_ms": round(t_f, 4), "bwd_ms": round(t_b, 4),
+        "fwd_GBs": round(24 * B * H * W / 1e9 / (t_f / 1e3), 1), "bwd_GBs": round(24 * B * H * W / 1e9 / (t_b / 1e3), 1),
+        "hbm_frac_fwd_bwd": round(48 * B * H * W / 1e9 / ((t_f + t_b) / 1e3) / peak, 3),
+        "MP_s_fwd_bwd_per_filter_application": round(S4 * B * H * W / 1e6 / ((t_f + t_b) / 1e3), 1)}
     # (a2) SURVEY §8(f)-1: the 64x64 block-mean image in one pass vs nn.AdaptiveAvgPool2d
     pool = torch.nn.AdaptiveAvgPool2d((64, 64))
     t_k, t_t = timed(lambda: AF.block_mean(img, (64, 64)), 10), timed(lambda: pool(img), 10)

@@ -53,6 +53,7 @@ enum aisp_op {
 #define AISP_PSTRIDE   24 /* floats per (sample, step) parameter row */
 #define AISP_MAX_STEPS 8  /* longest fused per-sample sequence        */
 #define AISP_ACC_STRIDE 32 /* floats per partial-sum row in the backward scratch */
+#define AISP_MAX_CHAIN_BWD 4 /* longest per-sample sequence differentiated in one fused pass */
 
 enum aisp_status {
     AISP_OK              = 0,
@@ -105,6 +106,21 @@ size_t aisp_bwd_scratch_bytes(int B, int H, int W);
 int aisp_pointwise_bwd(const float* img, const float* grad_out, const float* params, const int32_t* ops,
                        int B, int H, int W, int clip, float* grad_params, float* grad_img,
                        void* scratch, size_t scratch_bytes, void* stream);
+
+/*
+ * Backward of a fused per-sample SEQUENCE of per-pixel filters (the forward is aisp_pointwise_fwd with
+ * the same params / ops / seq_len / clip_each) in ONE pass over HBM: the chain is recomputed per
+ * pixel in registers and swept in reverse, so the traffic is that of a single-step backward however
+ * many stages are fused.  S <= AISP_MAX_CHAIN_BWD (longer chains: split them and pass grad_img on).
+ *   grad_params [B,S,AISP_PSTRIDE]   rows of steps >= seq_len[b] are zero
+ *   grad_img    [B,3,H,W] or NULL
+ * COLOR inside a fused backward sequence yields a NaN gradient row (27 partial sums do not fit the
+ * per-stage register budget); use the single-step aisp_pointwise_bwd for it.
+ */
+int aisp_pointwise_chain_bwd(const float* img, const float* grad_out, const float* params, const int32_t* ops,
+                             const int32_t* seq_len, int B, int H, int W, int S, int clip_each,
+                             float* grad_params, float* grad_img, void* scratch, size_t scratch_bytes,
+                             void* stream);
 
 /*
  * 3x3 sharpen (SHARPEN: adjust_sharpness isp/sharpen.py:105-142; SHARPEN_V2: sharpness :145-182)

@@ -32,7 +32,7 @@ def header_symbols():
 def test_library_exports_every_declared_symbol(lib):
     from adaptiveisp_b200 import _lib
     syms = header_symbols()
-    assert len(syms) == 14
+    assert len(syms) == 15
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/aisp_b200.h but not exported"
     assert set(syms) == set(_lib.SIGNATURES), "ctypes binding and header disagree"
@@ -43,7 +43,7 @@ def test_library_metadata_calls(lib):
     for op in range(13):
         assert lib.aisp_op_num_params(op) == O.OP_NPARAMS[op]
     assert lib.aisp_op_num_params(99) == -1
-    assert lib.aisp_bwd_scratch_bytes(64, 512, 512) == 64 * 128 * 32 * 4
+    assert lib.aisp_bwd_scratch_bytes(64, 512, 512) == 64 * 128 * 32 * 4 * 4    # x AISP_MAX_CHAIN_BWD
     assert lib.aisp_bwd_scratch_bytes(0, 512, 512) == 0
     assert b"NULL" in lib.aisp_status_string(-1)
     # argument validation happens before any CUDA call, so it is checkable without a GPU
