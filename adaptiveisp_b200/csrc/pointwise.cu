@@ -108,6 +108,36 @@ __device__ __forceinline__ void satplus_full(float r, float g, float b, float& f
     st.s = s; st.vv = vv; st.f = f; st.branch = branch; st.sextant = sx; st.satzero = satzero;
 }
 
+// Forward-only form of the same round trip: identical hue / saturation arithmetic, but hsv -> rgb
+// uses the branch-free k-form  c_n = v - v*s*sat(min(k, 4 - k)),  k = (n + 6h) mod 6,  n = 5, 3, 1
+// (algebraically the sextant table of isp/filters.py:505-527) -- 6 ALU-pipe ops instead of the
+// floor / float->int / 6-way select, which made this filter ALU-bound.  Results agree with the
+// table form to ~1 ulp; the backward keeps the table form because it needs the sextant for routing.
+__device__ __forceinline__ void satplus_forward(float r, float g, float b, float& fr, float& fg, float& fb) {
+    const float mx = fmaxf(r, fmaxf(g, b));
+    const float mn = fminf(r, fminf(g, b));
+    const float d = (mx - mn) + 1e-8f;
+    float num, base;
+    if (r == mx) { num = g - b; base = 0.0f; }
+    else if (g == mx) { num = b - r; base = 2.0f; }
+    else { num = r - g; base = 4.0f; }
+    const float q = __fdiv_rn(num, d);
+    float hue = base + q;
+    hue = (hue < 0.f) ? hue + 6.0f : hue;          // only the R branch can go negative: python-style % 6
+    if (mn == mx) hue = 0.f;
+    float h6 = div6(hue);                           // same rounding as the reference's hue / 6 ...
+    h6 = ((h6 >= 1.0f) ? h6 - 1.0f : h6) * 6.0f;    // ... then (h % 1) * 6
+    float sat = __fdividef(mx - mn, mx + 1e-8f);
+    if (mx == 0.f) sat = 0.f;
+    const float m = 0.5f - fabsf(0.5f - mx);
+    const float s = clip01(sat + (1.f - sat) * m * 0.8f);
+    const float nvs = -(mx * s);                    // v is already in [0,1]
+    float k;
+    k = h6 + 5.0f; k = (k >= 6.0f) ? k - 6.0f : k; fr = fmaf(nvs, __saturatef(fminf(k, 4.0f - k)), mx);
+    k = h6 + 3.0f; k = (k >= 6.0f) ? k - 6.0f : k; fg = fmaf(nvs, __saturatef(fminf(k, 4.0f - k)), mx);
+    k = h6 + 1.0f; k = (k >= 6.0f) ? k - 6.0f : k; fb = fmaf(nvs, __saturatef(fminf(k, 4.0f - k)), mx);
+}
+
 template <int NPX>
 __device__ __forceinline__ void fwd_step(int op, const float* __restrict__ c, float (&R)[NPX], float (&G)[NPX],
                                          float (&B)[NPX]) {
@@ -196,8 +226,7 @@ __device__ __forceinline__ void fwd_step(int op, const float* __restrict__ c, fl
         for (int i = 0; i < NPX; ++i) {
             const float r = clip01(R[i]), g = clip01(G[i]), b = clip01(B[i]);
             float fr, fg, fb;
-            HsvState st;
-            satplus_full(r, g, b, fr, fg, fb, st);
+            satplus_forward(r, g, b, fr, fg, fb);
             R[i] = r * ip + fr * p;
             G[i] = g * ip + fg * p;
             B[i] = b * ip + fb * p;
@@ -393,7 +422,8 @@ struct PwBwd<AISP_OP_SATPLUS> {
         const float r = clip01(r0), g = clip01(g0), b = clip01(b0);
         float fr, fg, fb;
         HsvState st;
-        satplus_full(r, g, b, fr, fg, fb, st);
+        if (GIMG) satplus_full(r, g, b, fr, fg, fb, st);     // the reverse sweep needs the sextant / f / s
+        else satplus_forward(r, g, b, fr, fg, fb);            // d y / d p = full - x only needs the colour
         AISP_MASK_CLIP(r * ip + fr * p, g * ip + fg * p, b * ip + fb * p)
         acc[0] = fmaf(gr, fr - r, fmaf(gg, fg - g, fmaf(gb, fb - b, acc[0])));
         if (GIMG) {
