@@ -33,7 +33,10 @@ __device__ __forceinline__ float curve8(float x, const float* c, int stride) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const float u = __saturatef(fmaf(x, 8.0f, -(float)k));
-        acc = acc + u * c[k * stride];
+        // fused multiply-add: bit-identical to ATen's separate multiply and add wherever the clamp
+        // mask could flip -- saturated (x >= 1) and dark (x <= 0) pixels have u_k in {0, 1}, whose
+        // products are exact -- and within 1 ulp elsewhere
+        acc = fmaf(u, c[k * stride], acc);
     }
     return acc;
 }
@@ -325,7 +328,7 @@ __device__ __forceinline__ void curve8_bwd(float x, const float* c, int stride, 
     for (int k = 0; k < 8; ++k) {
         v[k] = fmaf(x, 8.0f, -(float)k);
         u[k] = __saturatef(v[k]);
-        sum = sum + u[k] * c[k * stride];
+        sum = fmaf(u[k], c[k * stride], sum);
     }
     const float y = sum * (sc * 0.125f);
     if (clip) g *= pass01(y);
