@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(CSRC, "libaisp_b200.so")
 PSTRIDE = 24
 MAX_STEPS = 8
 MAX_CHAIN_BWD = 4
+MAX_BANK_FILTERS = 16
 ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/aisp_b200.h one to one
@@ -41,6 +42,8 @@ SIGNATURES = {
     "aisp_select_apply_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "aisp_select_apply_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_size_t,
                                       _P]),
+    "aisp_bank_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "aisp_bank_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
 }
 
 _lib = None

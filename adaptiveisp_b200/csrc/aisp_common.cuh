@@ -227,17 +227,41 @@ __device__ __forceinline__ void block_reduce_store(float (&acc)[N], float* red /
     }
 }
 
-// Second stage shared by every family: grid = B, block = kThreads.  Sums `nrows` scratch rows of
-// sample b in fp64 (fixed order), applies finalize_grads and writes grad_params[b, :].
-__global__ void finalize_kernel(const float* __restrict__ partial, int nrows, const float* __restrict__ params,
-                                const int32_t* __restrict__ ops, int family, float* __restrict__ grad_params);
-
 enum { FAMILY_POINTWISE = 0, FAMILY_SHARPEN = 1, FAMILY_NLM = 2 };
+
+// Filter-bank launches (aisp_bank_*): F filters applied to the same batch.  "Virtual sample"
+// v = image * F + slot indexes out / params / grad_out / grad_params / scratch; the image (and the
+// compact NLM stash) is indexed by v / F.  A family's launch only covers its own `n` slots: the
+// sample coordinate of the grid runs over image * n + j and `slots` (4 bits per entry) maps j to
+// the slot.  The op code of slot f is nibble f of `opsn` (the bank's op list lives on the host, so
+// there is no device-side ops array).  A plain batch is {F = 1, n = 0}: v = grid coordinate.
+constexpr int kMaxBankFilters = 16;
+struct BankMap {
+    int F;
+    int n;
+    unsigned long long slots;
+    unsigned long long opsn;
+};
+inline BankMap plain_batch() { return BankMap{1, 0, 0ull, 0ull}; }
+__device__ __forceinline__ int bank_sample(const BankMap& bm, int g) {
+    return bm.n == 0 ? g : (g / bm.n) * bm.F + (int)((bm.slots >> (4 * (g % bm.n))) & 15ull);
+}
+__device__ __forceinline__ int bank_op(const BankMap& bm, int v) { return (int)((bm.opsn >> (4 * (v % bm.F))) & 15ull); }
+// op of sample v (first step of its sequence when S > 1)
+__device__ __forceinline__ int sample_op(const int32_t* __restrict__ ops, const BankMap& bm, int v, int S = 1) {
+    return ops ? ops[(size_t)v * S] : bank_op(bm, v);
+}
 __host__ __device__ __forceinline__ bool in_family(int op, int family) {
     return family == FAMILY_POINTWISE ? is_pointwise(op)
          : family == FAMILY_SHARPEN   ? is_sharpen(op)
                                       : op == AISP_OP_NLM;
 }
+
+// Second stage shared by every family: grid = B, block = kThreads.  Sums `nrows` scratch rows of
+// sample b in fp64 (fixed order), applies finalize_grads and writes grad_params[b, :].
+__global__ void finalize_kernel(const float* __restrict__ partial, int nrows, const float* __restrict__ params,
+                                const int32_t* __restrict__ ops, int family, float* __restrict__ grad_params,
+                                BankMap bm);
 
 // launch geometry shared between kernels and aisp_bwd_scratch_bytes
 constexpr int kPwChunkPx = 4096;       // pixels per CTA in the per-pixel kernels

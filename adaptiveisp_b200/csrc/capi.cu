@@ -4,17 +4,17 @@
 
 namespace aisp {
 cudaError_t launch_pointwise_fwd(const float*, float*, const float*, const int32_t*, const int32_t*, int, int, int, int,
-                                 int, cudaStream_t);
+                                 int, BankMap, cudaStream_t);
 cudaError_t launch_pointwise_bwd(const float*, const float*, const float*, const int32_t*, int, int, int, int, float*,
-                                 float*, float*, cudaStream_t);
-cudaError_t launch_sharpen_fwd(const float*, float*, const float*, const int32_t*, int, int, int, cudaStream_t);
+                                 float*, float*, BankMap, cudaStream_t);
+cudaError_t launch_sharpen_fwd(const float*, float*, const float*, const int32_t*, int, int, int, BankMap, cudaStream_t);
 cudaError_t launch_sharpen_bwd(const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*,
-                               float*, float*, cudaStream_t);
-cudaError_t launch_nlm_fwd(const float*, float*, const float*, const int32_t*, int, int, int, float*, float*,
+                               float*, float*, BankMap, cudaStream_t);
+cudaError_t launch_nlm_fwd(const float*, float*, const float*, const int32_t*, int, int, int, float*, float*, BankMap,
                            cudaStream_t);
 cudaError_t launch_nlm_bwd_img(const float*, const float*, const float*, const float*, const float*, const int32_t*, int,
                                int, int, float*, cudaStream_t);
-cudaError_t launch_nlm_bwd(const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*,
+cudaError_t launch_nlm_bwd(const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*, BankMap,
                            cudaStream_t);
 cudaError_t launch_block_mean(const float*, float*, int, int, int, int, int, cudaStream_t);
 cudaError_t launch_pointwise_chain_bwd(const float*, const float*, const float*, const int32_t*, const int32_t*, int, int,
@@ -71,7 +71,7 @@ int aisp_pointwise_fwd(const float* img, float* out, const float* params, const 
     if (!shape_ok(B, H, W) || S < 1 || S > AISP_MAX_STEPS) return AISP_ERR_SHAPE;
     if (!al4(img) || !al4(out)) return AISP_ERR_ALIGN;
     if (img == out) return AISP_ERR_UNSUPPORTED;
-    return (int)launch_pointwise_fwd(img, out, params, ops, seq_len, B, H, W, S, clip_each ? 1 : 0,
+    return (int)launch_pointwise_fwd(img, out, params, ops, seq_len, B, H, W, S, clip_each ? 1 : 0, plain_batch(),
                                      (cudaStream_t)stream);
 }
 
@@ -83,7 +83,7 @@ int aisp_pointwise_bwd(const float* img, const float* grad_out, const float* par
     if (scratch_bytes < aisp_bwd_scratch_bytes(B, H, W)) return AISP_ERR_SCRATCH;
     if (!al4(img) || !al4(grad_out) || !al4(grad_img)) return AISP_ERR_ALIGN;
     return (int)launch_pointwise_bwd(img, grad_out, params, ops, B, H, W, clip ? 1 : 0, grad_params, grad_img,
-                                     (float*)scratch, (cudaStream_t)stream);
+                                     (float*)scratch, plain_batch(), (cudaStream_t)stream);
 }
 
 int aisp_pointwise_chain_bwd(const float* img, const float* grad_out, const float* params, const int32_t* ops,
@@ -103,7 +103,7 @@ int aisp_sharpen_fwd(const float* img, float* out, const float* params, const in
     if (!img || !out || !params || !ops) return AISP_ERR_NULL;
     if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
     if (img == out) return AISP_ERR_UNSUPPORTED;
-    return (int)launch_sharpen_fwd(img, out, params, ops, B, H, W, (cudaStream_t)stream);
+    return (int)launch_sharpen_fwd(img, out, params, ops, B, H, W, plain_batch(), (cudaStream_t)stream);
 }
 
 int aisp_sharpen_bwd(const float* img, const float* grad_out, const float* params, const int32_t* ops, int B, int H,
@@ -114,7 +114,7 @@ int aisp_sharpen_bwd(const float* img, const float* grad_out, const float* param
     if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
     if (scratch_bytes < aisp_bwd_scratch_bytes(B, H, W)) return AISP_ERR_SCRATCH;
     return (int)launch_sharpen_bwd(img, grad_out, params, ops, B, H, W, grad_params, grad_img, gy_scratch,
-                                   (float*)scratch, (cudaStream_t)stream);
+                                   (float*)scratch, plain_batch(), (cudaStream_t)stream);
 }
 
 int aisp_nlm_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,
@@ -122,7 +122,7 @@ int aisp_nlm_fwd(const float* img, float* out, const float* params, const int32_
     if (!img || !out || !params || !ops) return AISP_ERR_NULL;
     if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
     if (img == out) return AISP_ERR_UNSUPPORTED;
-    return (int)launch_nlm_fwd(img, out, params, ops, B, H, W, dout_dh, wsum, (cudaStream_t)stream);
+    return (int)launch_nlm_fwd(img, out, params, ops, B, H, W, dout_dh, wsum, plain_batch(), (cudaStream_t)stream);
 }
 
 int aisp_nlm_bwd(const float* grad_out, const float* dout_dh, const int32_t* ops, int B, int H, int W,
@@ -130,7 +130,7 @@ int aisp_nlm_bwd(const float* grad_out, const float* dout_dh, const int32_t* ops
     if (!grad_out || !dout_dh || !ops || !grad_params || !scratch) return AISP_ERR_NULL;
     if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
     if (scratch_bytes < aisp_bwd_scratch_bytes(B, H, W)) return AISP_ERR_SCRATCH;
-    return (int)launch_nlm_bwd(grad_out, dout_dh, nullptr, ops, B, H, W, grad_params, (float*)scratch,
+    return (int)launch_nlm_bwd(grad_out, dout_dh, nullptr, ops, B, H, W, grad_params, (float*)scratch, plain_batch(),
                                (cudaStream_t)stream);
 }
 
@@ -176,6 +176,70 @@ int aisp_select_apply_bwd(const float* img, const float* out, const float* grad_
     if (e) return e;
     if (grad_img) e = aisp_nlm_bwd_img(img, out, nlm_wsum, grad_out, params, ops, B, H, W, grad_img, stream);
     return e;
+}
+
+// ---- filter bank: F filters applied to the SAME batch (agent.py:103-107 runs every cfg.filter on
+// the input and stacks the results).  The op list is a HOST array; each family launches only over
+// its own slots (BankMap), so there are no idle CTAs and no device-side ops array.
+static int make_bank_maps(const int32_t* fops, int F, BankMap m[3]) {
+    if (F < 1 || F > kMaxBankFilters) return AISP_ERR_SHAPE;
+    unsigned long long opsn = 0;
+    for (int f = 0; f < F; ++f) {
+        if (fops[f] < 0 || fops[f] >= AISP_OP_COUNT) return AISP_ERR_UNSUPPORTED;
+        opsn |= (unsigned long long)fops[f] << (4 * f);
+    }
+    for (int k = 0; k < 3; ++k) m[k] = BankMap{F, 0, 0ull, opsn};
+    for (int f = 0; f < F; ++f) {
+        const int k = is_pointwise(fops[f]) ? FAMILY_POINTWISE : is_sharpen(fops[f]) ? FAMILY_SHARPEN : FAMILY_NLM;
+        m[k].slots |= (unsigned long long)f << (4 * m[k].n);
+        ++m[k].n;
+    }
+    return m[FAMILY_NLM].n > 1 ? AISP_ERR_UNSUPPORTED : AISP_OK;  // one compact stash per image
+}
+
+int aisp_bank_fwd(const float* img, float* out, const float* params, const int32_t* filter_ops, int B, int F, int H,
+                  int W, int clip, float* nlm_dout_dh, void* stream) {
+    if (!img || !out || !params || !filter_ops) return AISP_ERR_NULL;
+    if (!shape_ok(B, H, W) || F < 1 || (long long)B * F > 65535) return AISP_ERR_SHAPE;
+    if (!al4(img) || !al4(out)) return AISP_ERR_ALIGN;
+    if (img == out) return AISP_ERR_UNSUPPORTED;
+    BankMap m[3];
+    int rc = make_bank_maps(filter_ops, F, m);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSuccess;
+    if (m[FAMILY_POINTWISE].n)
+        e = launch_pointwise_fwd(img, out, params, nullptr, nullptr, B * m[FAMILY_POINTWISE].n, H, W, 1, clip ? 1 : 0,
+                                 m[FAMILY_POINTWISE], st);
+    if (e == cudaSuccess && m[FAMILY_SHARPEN].n)
+        e = launch_sharpen_fwd(img, out, params, nullptr, B * m[FAMILY_SHARPEN].n, H, W, m[FAMILY_SHARPEN], st);
+    if (e == cudaSuccess && m[FAMILY_NLM].n)
+        e = launch_nlm_fwd(img, out, params, nullptr, B * m[FAMILY_NLM].n, H, W, nlm_dout_dh, nullptr, m[FAMILY_NLM], st);
+    return (int)e;
+}
+
+int aisp_bank_bwd(const float* img, const float* grad_out, const float* params, const int32_t* filter_ops, int B,
+                  int F, int H, int W, int clip, const float* nlm_dout_dh, float* grad_params, void* scratch,
+                  size_t scratch_bytes, void* stream) {
+    if (!img || !grad_out || !params || !filter_ops || !grad_params || !scratch) return AISP_ERR_NULL;
+    if (!shape_ok(B, H, W) || F < 1 || (long long)B * F > 65535) return AISP_ERR_SHAPE;
+    if (scratch_bytes < aisp_bwd_scratch_bytes(B * F, H, W)) return AISP_ERR_SCRATCH;
+    if (!al4(img) || !al4(grad_out)) return AISP_ERR_ALIGN;
+    BankMap m[3];
+    int rc = make_bank_maps(filter_ops, F, m);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSuccess;
+    if (m[FAMILY_POINTWISE].n)
+        e = launch_pointwise_bwd(img, grad_out, params, nullptr, B * m[FAMILY_POINTWISE].n, H, W, clip ? 1 : 0,
+                                 grad_params, nullptr, (float*)scratch, m[FAMILY_POINTWISE], st);
+    if (e == cudaSuccess && m[FAMILY_SHARPEN].n)
+        e = launch_sharpen_bwd(img, grad_out, params, nullptr, B * m[FAMILY_SHARPEN].n, H, W, grad_params, nullptr,
+                               nullptr, (float*)scratch, m[FAMILY_SHARPEN], st);
+    if (e == cudaSuccess && m[FAMILY_NLM].n && nlm_dout_dh)
+        e = launch_nlm_bwd(grad_out, nlm_dout_dh, nullptr, nullptr, B * m[FAMILY_NLM].n, H, W, grad_params,
+                           (float*)scratch, m[FAMILY_NLM], st);
+    return (int)e;
 }
 
 }  // extern "C"

@@ -74,15 +74,16 @@ template <bool WITH_GRAD>
 __global__ void __launch_bounds__(kThreads, WITH_GRAD ? 3 : 4)
 nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __restrict__ dout_dh,
            float* __restrict__ wsum_out, const float* __restrict__ params, const int32_t* __restrict__ ops, int H,
-           int W) {
+           int W, BankMap bm) {
     pdl_prologue();
     __shared__ float sY[kNlmSmH][kNlmSmW];
     __shared__ float sC[3][kNlmSmH][kNlmSmW];
-    const int b = blockIdx.z;
-    if (ops[b] != AISP_OP_NLM) return;
+    const int b = bank_sample(bm, blockIdx.z);   // filter-bank launches: see BankMap
+    if (sample_op(ops, bm, b) != AISP_OP_NLM) return;
     const int x0 = blockIdx.x * kNlmTileW, y0 = blockIdx.y * kNlmTileH;
     const size_t plane = (size_t)H * W;
-    const float* src = img + (size_t)b * 3 * plane;
+    const float* src = img + (size_t)(b / bm.F) * 3 * plane;
+    const size_t sb = (size_t)(b / bm.F);        // stashes stay compact: one NLM slot per image
 
     // stage clipped RGB and luma of the wrapped tile + halo       (isp/filters.py:583, denoise.py:11-17)
     // a warp walks whole rows (row wrap once per row, column wrap by one conditional add when the
@@ -211,13 +212,15 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
         const int gy = y0 + r0 + i;
         if (gy >= H) continue;
         const float iw = 1.0f / wsum[i];
-        if (wsum_out) wsum_out[(size_t)b * plane + (size_t)gy * W + gx] = wsum[i];
+        if (wsum_out) wsum_out[sb * plane + (size_t)gy * W + gx] = wsum[i];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float y = ac[c][i] * iw;
             const size_t o = (size_t)b * 3 * plane + (size_t)c * plane + (size_t)gy * W + gx;
             out[o] = clip01(y);
-            if (WITH_GRAD) dout_dh[o] = pass01(y) * (bc[c][i] - y * wd[i]) * iw * inv_h2;
+            if (WITH_GRAD)
+                dout_dh[sb * 3 * plane + (size_t)c * plane + (size_t)gy * W + gx] =
+                    pass01(y) * (bc[c][i] - y * wd[i]) * iw * inv_h2;
         }
     }
 }
@@ -225,13 +228,13 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
 // grad_h[b] = sum g * dout_dh : plain streaming dot product, chunked like the per-pixel kernels
 __global__ void __launch_bounds__(kThreads)
 nlm_dot_kernel(const float* __restrict__ gout, const float* __restrict__ stash, const int32_t* __restrict__ ops,
-               long long n /* 3*H*W */, float* __restrict__ partial) {
+               long long n /* 3*H*W */, float* __restrict__ partial, BankMap bm) {
     pdl_prologue();
     __shared__ float red[kWarps * AISP_ACC_STRIDE];
-    const int b = blockIdx.y;
-    if (ops[b] != AISP_OP_NLM) return;
+    const int b = bank_sample(bm, blockIdx.y);
+    if (sample_op(ops, bm, b) != AISP_OP_NLM) return;
     const float* g = gout + (size_t)b * n;
-    const float* s = stash + (size_t)b * n;
+    const float* s = stash + (size_t)(b / bm.F) * n;
     float acc[1] = {0.f};
     const long long lo = (long long)blockIdx.x * (3 * kPwChunkPx);
     const long long hi = min(lo + 3 * kPwChunkPx, n);
@@ -247,16 +250,16 @@ nlm_dot_kernel(const float* __restrict__ gout, const float* __restrict__ stash, 
 }
 
 cudaError_t launch_finalize(const float* partial, int nrows, const float* params, const int32_t* ops, int family,
-                            int B, float* grad_params, cudaStream_t st);
+                            int B, float* grad_params, BankMap bm, cudaStream_t st);
 int pointwise_rows(int H, int W);
 
 cudaError_t launch_nlm_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,
-                           float* dout_dh, float* wsum, cudaStream_t st) {
+                           float* dout_dh, float* wsum, BankMap bm, cudaStream_t st) {
     dim3 grid((W + kNlmTileW - 1) / kNlmTileW, (H + kNlmTileH - 1) / kNlmTileH, B);
     if (dout_dh)
-        launch_pdl(nlm_kernel<true>, grid, kThreads, st, img, out, dout_dh, wsum, params, ops, H, W);
+        launch_pdl(nlm_kernel<true>, grid, kThreads, st, img, out, dout_dh, wsum, params, ops, H, W, bm);
     else
-        launch_pdl(nlm_kernel<false>, grid, kThreads, st, img, out, nullptr, wsum, params, ops, H, W);
+        launch_pdl(nlm_kernel<false>, grid, kThreads, st, img, out, nullptr, wsum, params, ops, H, W, bm);
     return cudaGetLastError();
 }
 
@@ -383,16 +386,16 @@ cudaError_t launch_nlm_bwd_img(const float* img, const float* out, const float* 
 }
 
 cudaError_t launch_nlm_bwd(const float* gout, const float* stash, const float* params_unused, const int32_t* ops,
-                           int B, int H, int W, float* grad_params, float* partial, cudaStream_t st) {
+                           int B, int H, int W, float* grad_params, float* partial, BankMap bm, cudaStream_t st) {
     (void)params_unused;
     const int rows = pointwise_rows(H, W);
     dim3 grid(rows, B);
-    launch_pdl(nlm_dot_kernel, grid, kThreads, st, gout, stash, ops, 3LL * H * W, partial);
+    launch_pdl(nlm_dot_kernel, grid, kThreads, st, gout, stash, ops, 3LL * H * W, partial, bm);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // finalize reads params only to derive constants; NLM needs none, so grad_params doubles as a
     // valid readable buffer of the right shape
-    return launch_finalize(partial, rows, grad_params, ops, FAMILY_NLM, B, grad_params, st);
+    return launch_finalize(partial, rows, grad_params, ops, FAMILY_NLM, B, grad_params, bm, st);
 }
 
 }  // namespace aisp

@@ -483,7 +483,7 @@ struct PwBwd<AISP_OP_SATPLUS> {
 // =============================================================================================
 __device__ __forceinline__ void stage_consts(const float* __restrict__ params, const int32_t* __restrict__ ops,
                                              int b, int S, int len, float (*raw)[kConst], float (*sc)[kConst],
-                                             int* sop) {
+                                             int* sop, const BankMap& bm) {
     // one warp per step loads the raw row, lane 0 derives the constants
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp < len) {
@@ -491,7 +491,7 @@ __device__ __forceinline__ void stage_consts(const float* __restrict__ params, c
         sc[warp][lane] = 0.f;
         __syncwarp();
         if (lane == 0) {
-            const int op = ops[(size_t)b * S + warp];
+            const int op = ops ? ops[(size_t)b * S + warp] : bank_op(bm, b);
             sop[warp] = op;
             derive_consts(op, raw[warp], sc[warp]);
         }
@@ -502,18 +502,20 @@ __device__ __forceinline__ void stage_consts(const float* __restrict__ params, c
 template <int VEC>
 __global__ void __launch_bounds__(kThreads, 4)
 pw_fwd_kernel(const float* __restrict__ img, float* __restrict__ out, const float* __restrict__ params,
-              const int32_t* __restrict__ ops, const int32_t* __restrict__ seq_len, int N, int S, int clip_each) {
+              const int32_t* __restrict__ ops, const int32_t* __restrict__ seq_len, int N, int S, int clip_each,
+              BankMap bm) {
     pdl_prologue();
     static_assert(AISP_MAX_STEPS <= kWarps, "one warp per step stages the constants");
     __shared__ float raw[AISP_MAX_STEPS][kConst];
     __shared__ float sc[AISP_MAX_STEPS][kConst];
     __shared__ int sop[AISP_MAX_STEPS];
-    const int b = blockIdx.y;
+    const int b = bank_sample(bm, blockIdx.y);
     int len = seq_len ? min(max(seq_len[b], 0), S) : S;
-    if (len > 0 && !is_pointwise(ops[(size_t)b * S])) {
+    const int op0 = sample_op(ops, bm, b, S);
+    if (len > 0 && !is_pointwise(op0)) {
         // another family owns this sample -- except AISP_OP_NONE: the all-zero one-hot row of
         // agent.py:18-23,154 (pdf_sample returned -1), whose gathered image is exactly zero
-        if (ops[(size_t)b * S] == AISP_OP_NONE) {
+        if (op0 == AISP_OP_NONE) {
             float* q = out + (size_t)b * 3 * (size_t)N;
             const int c0 = blockIdx.x * kPwChunkPx;
             for (int pl = 0; pl < 3; ++pl)
@@ -521,7 +523,7 @@ pw_fwd_kernel(const float* __restrict__ img, float* __restrict__ out, const floa
         }
         return;
     }
-    stage_consts(params, ops, b, S, len, raw, sc, sop);
+    stage_consts(params, ops, b, S, len, raw, sc, sop, bm);
     // a stencil op inside a sequence terminates it (documented in the header)
     for (int k = 0; k < len; ++k)
         if (!is_pointwise(sop[k])) { len = k; break; }
@@ -529,8 +531,10 @@ pw_fwd_kernel(const float* __restrict__ img, float* __restrict__ out, const floa
     constexpr int GROUPS = kPwChunkPx / (kThreads * VEC);
     constexpr int G = (VEC == 4) ? 2 : 8;  // 8 px per thread per round, 4 CTAs/SM: TLP hides the load->compute->store phases
     constexpr int NPX = G * VEC;
+    // filter-bank launches (BankMap): outputs and parameters are indexed by the virtual sample b,
+    // the image by b / F; the slots of one image are neighbours in the grid and share it through L2
     const size_t base = (size_t)b * 3 * (size_t)N;
-    const float* pr = img + base;
+    const float* pr = img + (size_t)(b / bm.F) * 3 * (size_t)N;
     float* qr = out + base;
     const int chunk0 = blockIdx.x * kPwChunkPx;
 
@@ -628,14 +632,14 @@ template <int VEC, bool GIMG>
 __global__ void __launch_bounds__(kThreads, 4)
 pw_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, const float* __restrict__ params,
               const int32_t* __restrict__ ops, int N, int clip, float* __restrict__ gimg,
-              float* __restrict__ partial) {
+              float* __restrict__ partial, BankMap bm) {
     pdl_prologue();
     __shared__ float raw[1][kConst];
     __shared__ float sc[1][kConst];
     __shared__ int sop[1];
     __shared__ float red[kWarps * AISP_ACC_STRIDE];
-    const int b = blockIdx.y;
-    const int op = ops[b];
+    const int b = bank_sample(bm, blockIdx.y);
+    const int op = sample_op(ops, bm, b);
     if (!is_pointwise(op)) {
         if (GIMG && op == AISP_OP_NONE) {  // zero image -> zero gradient
             float* q = gimg + (size_t)b * 3 * (size_t)N;
@@ -645,9 +649,9 @@ pw_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, con
         }
         return;
     }
-    stage_consts(params, ops, b, 1, 1, raw, sc, sop);
+    stage_consts(params, ops, b, 1, 1, raw, sc, sop, bm);
     const size_t base = (size_t)b * 3 * (size_t)N;
-    const float* pr = img + base;
+    const float* pr = img + (size_t)(b / bm.F) * 3 * (size_t)N;
     const float* pg = gout + base;
     float* gi = GIMG ? gimg + base : nullptr;
     float* dst = partial + ((size_t)b * gridDim.x + blockIdx.x) * AISP_ACC_STRIDE;
@@ -671,14 +675,14 @@ pw_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, con
 
 __global__ void __launch_bounds__(kThreads)
 finalize_kernel(const float* __restrict__ partial, int nrows, const float* __restrict__ params,
-                const int32_t* __restrict__ ops, int family, float* __restrict__ grad_params) {
+                const int32_t* __restrict__ ops, int family, float* __restrict__ grad_params, BankMap bm) {
     pdl_prologue();
     __shared__ double part[kWarps][AISP_ACC_STRIDE];
     __shared__ double tot[AISP_ACC_STRIDE];
     __shared__ float raw[kConst];
     __shared__ float c[kConst];
-    const int b = blockIdx.x;
-    const int op = ops[b];
+    const int b = bank_sample(bm, blockIdx.x);
+    const int op = sample_op(ops, bm, b);
     if (!in_family(op, family)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* rows = partial + (size_t)b * nrows * AISP_ACC_STRIDE;
@@ -711,47 +715,47 @@ finalize_kernel(const float* __restrict__ partial, int nrows, const float* __res
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 cudaError_t launch_pointwise_fwd(const float* img, float* out, const float* params, const int32_t* ops,
-                                 const int32_t* seq_len, int B, int H, int W, int S, int clip_each,
+                                 const int32_t* seq_len, int B, int H, int W, int S, int clip_each, BankMap bm,
                                  cudaStream_t st) {
     const long long N = (long long)H * W;
     dim3 grid((unsigned)((N + kPwChunkPx - 1) / kPwChunkPx), (unsigned)B);
     const bool vec = (N % 4 == 0) && aligned16(img) && aligned16(out);
     if (vec)
-        launch_pdl(pw_fwd_kernel<4>, grid, kThreads, st, img, out, params, ops, seq_len, (int)N, S, clip_each);
+        launch_pdl(pw_fwd_kernel<4>, grid, kThreads, st, img, out, params, ops, seq_len, (int)N, S, clip_each, bm);
     else
-        launch_pdl(pw_fwd_kernel<1>, grid, kThreads, st, img, out, params, ops, seq_len, (int)N, S, clip_each);
+        launch_pdl(pw_fwd_kernel<1>, grid, kThreads, st, img, out, params, ops, seq_len, (int)N, S, clip_each, bm);
     return cudaGetLastError();
 }
 
 int pointwise_rows(int H, int W) { return (int)(((long long)H * W + kPwChunkPx - 1) / kPwChunkPx); }
 
 cudaError_t launch_finalize(const float* partial, int nrows, const float* params, const int32_t* ops, int family,
-                            int B, float* grad_params, cudaStream_t st) {
-    launch_pdl(finalize_kernel, B, kThreads, st, partial, nrows, params, ops, family, grad_params);
+                            int B, float* grad_params, BankMap bm, cudaStream_t st) {
+    launch_pdl(finalize_kernel, B, kThreads, st, partial, nrows, params, ops, family, grad_params, bm);
     return cudaGetLastError();
 }
 
 cudaError_t launch_pointwise_bwd(const float* img, const float* gout, const float* params, const int32_t* ops,
                                  int B, int H, int W, int clip, float* grad_params, float* grad_img,
-                                 float* partial, cudaStream_t st) {
+                                 float* partial, BankMap bm, cudaStream_t st) {
     const long long N = (long long)H * W;
     const int rows = pointwise_rows(H, W);
     dim3 grid((unsigned)rows, (unsigned)B);
     const bool vec = (N % 4 == 0) && aligned16(img) && aligned16(gout) && (!grad_img || aligned16(grad_img));
     if (vec) {
         if (grad_img)
-            launch_pdl(pw_bwd_kernel<4, true>, grid, kThreads, st, img, gout, params, ops, (int)N, clip, grad_img, partial);
+            launch_pdl(pw_bwd_kernel<4, true>, grid, kThreads, st, img, gout, params, ops, (int)N, clip, grad_img, partial, bm);
         else
-            launch_pdl(pw_bwd_kernel<4, false>, grid, kThreads, st, img, gout, params, ops, (int)N, clip, nullptr, partial);
+            launch_pdl(pw_bwd_kernel<4, false>, grid, kThreads, st, img, gout, params, ops, (int)N, clip, nullptr, partial, bm);
     } else {
         if (grad_img)
-            launch_pdl(pw_bwd_kernel<1, true>, grid, kThreads, st, img, gout, params, ops, (int)N, clip, grad_img, partial);
+            launch_pdl(pw_bwd_kernel<1, true>, grid, kThreads, st, img, gout, params, ops, (int)N, clip, grad_img, partial, bm);
         else
-            launch_pdl(pw_bwd_kernel<1, false>, grid, kThreads, st, img, gout, params, ops, (int)N, clip, nullptr, partial);
+            launch_pdl(pw_bwd_kernel<1, false>, grid, kThreads, st, img, gout, params, ops, (int)N, clip, nullptr, partial, bm);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    return launch_finalize(partial, rows, params, ops, FAMILY_POINTWISE, B, grad_params, st);
+    return launch_finalize(partial, rows, params, ops, FAMILY_POINTWISE, B, grad_params, bm, st);
 }
 
 // =============================================================================================
@@ -822,7 +826,7 @@ pw_chain_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gou
         }
         return;
     }
-    stage_consts(params, ops, b, S, len, raw, sc, sop);
+    stage_consts(params, ops, b, S, len, raw, sc, sop, BankMap{1, 0, 0ull, 0ull});
     for (int k = 0; k < len; ++k)
         if (!is_pointwise(sop[k])) { len = k; break; }
 

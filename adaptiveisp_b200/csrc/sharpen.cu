@@ -185,14 +185,14 @@ template <bool BWD, bool WRITE_GY>
 __global__ void __launch_bounds__(kThreads, BWD ? 3 : 4)
 sharpen_kernel(const __grid_constant__ CUtensorMap tmap, int tma_ok, const float* __restrict__ img,
                const float* __restrict__ gout, float* __restrict__ out, const float* __restrict__ params,
-               const int32_t* __restrict__ ops, int H, int W, int vec, float* __restrict__ partial) {
+               const int32_t* __restrict__ ops, int H, int W, int vec, float* __restrict__ partial, BankMap bm) {
     pdl_prologue();
     __shared__ __align__(128) float sm[kSmFloats];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ float sc[kConst];
     __shared__ float red[kWarps * AISP_ACC_STRIDE];
-    const int b = blockIdx.z;
-    const int op = ops[b];
+    const int b = bank_sample(bm, blockIdx.z);   // filter-bank launches: see BankMap
+    const int op = sample_op(ops, bm, b);
     if (!is_sharpen(op)) return;
     const int x0 = blockIdx.x * kShTileW, y0 = blockIdx.y * kShTileH;
     const size_t base = (size_t)b * 3 * H * W;
@@ -204,10 +204,10 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, int tma_ok, const float
         __syncthreads();
         if (threadIdx.x == 0) {
             mbar_expect_tx(&bar, kTmaBytes);
-            tma_load_3d(sm, &tmap, x0 - kColOff, y0 - kHalo, b * 3, &bar);
+            tma_load_3d(sm, &tmap, x0 - kColOff, y0 - kHalo, (b / bm.F) * 3, &bar);
         }
     } else {
-        stage_tile_cp(img + base, sm, H, W, x0, y0, vec != 0);
+        stage_tile_cp(img + (size_t)(b / bm.F) * 3 * H * W, sm, H, W, x0, y0, vec != 0);
     }
     load_consts(params, b, op, sc);
 
@@ -407,7 +407,7 @@ int sharpen_rows(int H, int W) {
 }
 
 cudaError_t launch_finalize(const float* partial, int nrows, const float* params, const int32_t* ops, int family,
-                            int B, float* grad_params, cudaStream_t st);
+                            int B, float* grad_params, BankMap bm, cudaStream_t st);
 
 // [B*3, H, W] fp32 tensor map with a 3 x 20 x 136 box.  Returns false when TMA cannot describe the
 // image (rows not a multiple of 16 bytes, unaligned base, too many planes) -> cp.async path.
@@ -443,32 +443,32 @@ static bool make_tile_map(CUtensorMap* map, const float* img, int B, int H, int 
 }
 
 cudaError_t launch_sharpen_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H,
-                               int W, cudaStream_t st) {
+                               int W, BankMap bm, cudaStream_t st) {
     dim3 grid((W + kShTileW - 1) / kShTileW, (H + kShTileH - 1) / kShTileH, B);
     const int vec = ((W & 3) == 0) && al16(img) && al16(out);
     CUtensorMap map;
-    const int tma_ok = make_tile_map(&map, img, B, H, W) ? 1 : 0;
+    const int tma_ok = make_tile_map(&map, img, bm.n ? B / bm.n : B, H, W) ? 1 : 0;
     launch_pdl(sharpen_kernel<false, false>, grid, kThreads, st, map, tma_ok, img, nullptr, out, params, ops, H, W, vec,
-                                                            nullptr);
+                                                            nullptr, bm);
     return cudaGetLastError();
 }
 
 cudaError_t launch_sharpen_bwd(const float* img, const float* gout, const float* params, const int32_t* ops, int B,
                                int H, int W, float* grad_params, float* grad_img, float* gy_scratch, float* partial,
-                               cudaStream_t st) {
+                               BankMap bm, cudaStream_t st) {
     dim3 grid((W + kShTileW - 1) / kShTileW, (H + kShTileH - 1) / kShTileH, B);
     const int vec = ((W & 3) == 0) && al16(img) && al16(gout) && (!grad_img || al16(gy_scratch));
     CUtensorMap map;
-    const int tma_ok = make_tile_map(&map, img, B, H, W) ? 1 : 0;
+    const int tma_ok = make_tile_map(&map, img, bm.n ? B / bm.n : B, H, W) ? 1 : 0;
     if (grad_img)
         launch_pdl(sharpen_kernel<true, true>, grid, kThreads, st, map, tma_ok, img, gout, gy_scratch, params, ops, H, W, vec,
-                                                              partial);
+                                                              partial, bm);
     else
         launch_pdl(sharpen_kernel<true, false>, grid, kThreads, st, map, tma_ok, img, gout, nullptr, params, ops, H, W, vec,
-                                                               partial);
+                                                               partial, bm);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    e = launch_finalize(partial, sharpen_rows(H, W), params, ops, FAMILY_SHARPEN, B, grad_params, st);
+    e = launch_finalize(partial, sharpen_rows(H, W), params, ops, FAMILY_SHARPEN, B, grad_params, bm, st);
     if (e != cudaSuccess) return e;
     if (grad_img) {
         dim3 g2((W + kAdjW - 1) / kAdjW, (H + kAdjH - 1) / kAdjH, B);

@@ -25,7 +25,7 @@ from . import functional as AF
 __all__ = [
     "Filter", "ExposureFilter", "GammaFilter", "ImprovedWhiteBalanceFilter", "ColorFilter", "ToneFilter",
     "ToneFilterV2", "ContrastFilter", "WNBFilter", "SaturationPlusFilter", "DenoiseFilter", "SharpenUSMFilter",
-    "SharpenFilter", "SharpenFilterV2", "CCMFilter", "tanh01", "tanh_range", "lerp", "rgb2lum",
+    "SharpenFilter", "SharpenFilterV2", "CCMFilter", "FilterBank", "tanh01", "tanh_range", "lerp", "rgb2lum",
 ]
 
 
@@ -350,3 +350,48 @@ class CCMFilter(Filter):  # isp/filters.py:694-708
 
     def filter_param_regressor(self, features):
         return tanh_range(*self.cfg.ccm_range)(features)
+
+
+class FilterBank:
+    """Every filter of a list applied to the same batch in one banked launch set.
+
+    Equivalent to the run-all loop of the reference's agent (agent.py:103-107)::
+
+        stack = torch.stack([f(img, img_features)[0] for f in filters], dim=1)      # [B,F,3,H,W]
+
+    but the image arithmetic of all F filters is three kernel launches (``functional.apply_bank``)
+    instead of F, and the F reads of the image share L2.  Parameter regression stays per filter
+    (the FC layers differ); ``filters`` are the already constructed drop-in modules, so their
+    weights / ``state_dict`` are untouched.  Not an ``nn.Module``: it owns no parameters.
+    """
+
+    def __init__(self, filters):
+        self.filters = list(filters)
+        if not self.filters:
+            raise ValueError("empty filter bank")
+        for f in self.filters:
+            if f.use_masking():
+                raise NotImplementedError("spatial masking is dead code in the reference and is not part of the hot path")
+        self.ops = [int(f.OP) for f in self.filters]
+
+    def parameters_for(self, img_features=None, specified_parameters=None):
+        """-> list of per-filter parameter tensors in the reference's own layouts."""
+        assert (img_features is None) ^ (specified_parameters is None)
+        if specified_parameters is not None:
+            assert len(specified_parameters) == len(self.filters)
+            return list(specified_parameters)
+        out = []
+        for f in self.filters:
+            feats, _ = f.extract_parameters(img_features)
+            out.append(f.filter_param_regressor(feats))
+        return out
+
+    def __call__(self, img, img_features=None, specified_parameters=None, clip=True):
+        """-> (stack ``[B,F,3,H,W]``, list of debug_info dicts as ``Filter.forward`` returns them)."""
+        params = self.parameters_for(img_features, specified_parameters)
+        P = torch.stack([AF.pack_params(p, f.get_num_filter_parameters()) for p, f in zip(params, self.filters)], dim=1)
+        stack = AF.apply_bank(img, P, self.ops, clip=clip)
+        debug = []
+        for p, f in zip(params, self.filters):
+            debug.append({"filter_parameters": f._debug(p), "mask": f.get_mask(img)[0]})
+        return stack, debug

@@ -7,6 +7,7 @@ fused multi-step forward used for fixed chains and saved-pipeline replay.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Optional, Sequence
 
 import torch
@@ -147,6 +148,73 @@ def apply_ops(img: torch.Tensor, P: torch.Tensor, ops, clip: bool, family: Optio
 def apply_filter(img: torch.Tensor, param: torch.Tensor, op: int, clip: bool) -> torch.Tensor:
     """One filter class on the whole batch; ``param`` in the reference's own layout."""
     return apply_ops(img, pack_params(param, NUM_PARAMS[op]), op, clip, family_of(op))
+
+
+class _ApplyBank(torch.autograd.Function):
+    """stack[b, f] = [clip](process_{ops[f]}(img[b], P[b, f])) for F filters on the same batch."""
+
+    @staticmethod
+    def forward(ctx, img, P, ops, clip: bool):
+        _lib.require_image(img, "img")
+        B, _, H, W = img.shape
+        F = len(ops)
+        has_nlm = OP_NLM in ops
+        ops_c = (ctypes.c_int32 * F)(*ops)          # host array: the bank's op list never lives on the device
+        if ctx.needs_input_grad[0]:
+            raise _lib.AispError("apply_bank differentiates w.r.t. the filter parameters only; "
+                                 "detach the image (train.py:255) or use apply_ops per filter")
+        out = torch.empty((B, F, 3, H, W), dtype=torch.float32, device=img.device)
+        stash = torch.empty_like(img) if (has_nlm and ctx.needs_input_grad[1]) else None
+        with torch.cuda.device(img.device):
+            rc = _lib.lib().aisp_bank_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), ops_c, B, F, H, W,
+                                          int(clip), _lib.ptr(stash), _lib.stream_ptr(img.device))
+        _lib.check(rc, "aisp_bank_fwd")
+        ctx.save_for_backward(img, P, stash)
+        ctx.clip = bool(clip)
+        ctx.ops_c = ops_c
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        img, P, stash = ctx.saved_tensors
+        if not ctx.needs_input_grad[1]:
+            return None, None, None, None
+        B, _, H, W = img.shape
+        F = len(ctx.ops_c)
+        g = g.contiguous()
+        if g.dtype != torch.float32:
+            raise _lib.AispError("grad_out must be float32")
+        gP = torch.zeros_like(P)
+        sc = _lib.scratch(B * F, H, W, img.device)
+        with torch.cuda.device(img.device):
+            rc = _lib.lib().aisp_bank_bwd(img.data_ptr(), g.data_ptr(), P.data_ptr(), ctx.ops_c, B, F, H, W,
+                                          int(ctx.clip), _lib.ptr(stash), gP.data_ptr(), sc.data_ptr(), sc.numel(),
+                                          _lib.stream_ptr(img.device))
+        _lib.check(rc, "aisp_bank_bwd")
+        return None, gP, None, None
+
+
+def apply_bank(img: torch.Tensor, P: torch.Tensor, ops: Sequence[int], clip: bool = True) -> torch.Tensor:
+    """All of ``ops`` (F op codes) applied to the same batch, results stacked on dim 1 -- the
+    ``torch.stack([f(img, ...) for f in filters], dim=1)`` of agent.py:103-107 -- in three launches
+    (one per kernel family) whose F reads of every image chunk share L2.
+
+    img ``[B,3,H,W]`` (no gradient flows to it); P ``[B,F,PSTRIDE]`` packed rows (may require grad);
+    returns ``[B,F,3,H,W]``.  At most one NLM entry in ``ops`` (its d/dh stash is kept compact).
+    """
+    ops = tuple(int(o) for o in ops)
+    B, F = img.shape[0], len(ops)
+    if not (1 <= F <= _lib.MAX_BANK_FILTERS) or B * F > 65535:
+        raise _lib.AispError(f"bank of {F} filters on a batch of {B}: need 1 <= F <= {_lib.MAX_BANK_FILTERS} "
+                             "and B*F <= 65535")
+    if P.shape != (B, F, PSTRIDE) or P.dtype != torch.float32 or not P.is_cuda:
+        raise _lib.AispError(f"P must be CUDA float32 [B,F,{PSTRIDE}], got {tuple(P.shape)} {P.dtype}")
+    if any(not (0 <= o < len(NUM_PARAMS)) for o in ops):
+        raise _lib.AispError(f"unknown op code in {ops}")
+    n_nlm = sum(1 for o in ops if o == OP_NLM)
+    if n_nlm > 1:
+        raise _lib.AispError("a filter bank holds at most one NLM filter")
+    return _ApplyBank.apply(img, P.contiguous(), ops, clip)
 
 
 class _ApplyChain(torch.autograd.Function):

@@ -12,7 +12,9 @@ LOD-shaped 512x512 frames per GPU.  One "step" = those 10 filter applications fw
 per step = 10 * B * H * W / 1e6.  This is what the reference's Agent.forward + backward does to the
 ISP filters in one training iteration (agent.py:103-109 runs all ten on the whole batch).
 
-  value  : resident inputs, straight through the C ABI (ctypes -> libaisp_b200.so)
+  value  : resident inputs, straight through the C ABI (ctypes -> libaisp_b200.so): one
+           aisp_bank_fwd + one aisp_bank_bwd per step (all ten filters on the batch, outputs stacked
+           [B,10,3,H,W] as agent.py:103-107 does, a distinct upstream gradient per filter)
   e2e    : through the drop-in Filter classes (FC layers + regressors + autograd + kernels) with
            the image batch coming from pinned HOST memory every step and one output batch going
            back to the host every step (train.py:255 / :378-381)
@@ -239,7 +241,27 @@ def run_b200(args):
         _lib.check(rc, "bwd " + names[i])
 
     nf = len(flts)
-    launches_per_step = nf * 3  # fwd kernel + bwd kernel + finalize kernel per filter
+    # ---- the filter bank: all ten filters on the batch in one call each way ----
+    import ctypes
+    P_all = torch.stack(packed, 1).contiguous()                                 # [B,F,24]
+    bank_ops = (ctypes.c_int32 * nf)(*[f.OP for f in flts])                     # host op list
+    out_all = torch.empty((B, nf, 3, H, W), device=dev)
+    gout_all = torch.randn(out_all.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(8))
+    gP_all = torch.zeros((B, nf, 24), device=dev)
+    scratch_all = _lib.scratch(B * nf, H, W, dev)
+    scratch = scratch_all
+
+    def bank_fwd():
+        _lib.check(L.aisp_bank_fwd(img.data_ptr(), out_all.data_ptr(), P_all.data_ptr(), bank_ops, B, nf, H, W, 1,
+                                   stash.data_ptr(), st), "bank fwd")
+
+    def bank_bwd():
+        _lib.check(L.aisp_bank_bwd(img.data_ptr(), gout_all.data_ptr(), P_all.data_ptr(), bank_ops, B, nf, H, W, 1,
+                                   stash.data_ptr(), gP_all.data_ptr(), scratch_all.data_ptr(), scratch_all.numel(),
+                                   st), "bank bwd")
+
+    # 3 family kernels forward; 3 family kernels + 3 finalize kernels backward
+    launches_per_step = 9
 
     def barrier():
         if world > 1:
@@ -248,16 +270,36 @@ def run_b200(args):
 
     # ---------------- value: resident inputs, C ABI ----------------
     for _ in range(max(args.warmup, 3)):
-        for i in range(nf):
-            fwd(i)
-            bwd(i)
-    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-            torch.cuda.Event(enable_timing=True)) for _ in range(nf)] for _ in range(args.steps)]
+        bank_fwd()
+        bank_bwd()
+    sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     tw0 = time.time()
     e0.record()
     for s in range(args.steps):
+        a, b_, c = sev[s]
+        a.record()
+        bank_fwd()
+        b_.record()
+        bank_bwd()
+        c.record()
+    e1.record()
+    barrier()
+    tw1 = time.time()
+    seg_fwd = sum(a.elapsed_time(b_) for a, b_, _ in sev) / args.steps
+    seg_bwd = sum(b_.elapsed_time(c) for _, b_, c in sev) / args.steps
+
+    # per-filter breakdown: the same kernels launched one filter at a time (plain-batch entry points;
+    # every launch streams the image from HBM), a few iterations right after the timed region
+    k_iters = max(3, min(args.steps, 10))
+    for i in range(nf):
+        fwd(i)
+        bwd(i)
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+            torch.cuda.Event(enable_timing=True)) for _ in range(nf)] for _ in range(k_iters)]
+    for s in range(k_iters):
         for i in range(nf):
             a, b_, c = ev[s][i]
             a.record()
@@ -265,9 +307,7 @@ def run_b200(args):
             b_.record()
             bwd(i)
             c.record()
-    e1.record()
-    barrier()
-    tw1 = time.time()
+    torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -279,8 +319,8 @@ def run_b200(args):
     # per-kernel durations from the events recorded inside the timed region
     kern = {}
     for i in range(nf):
-        tf = sum(ev[s][i][0].elapsed_time(ev[s][i][1]) for s in range(args.steps)) / args.steps
-        tb = sum(ev[s][i][1].elapsed_time(ev[s][i][2]) for s in range(args.steps)) / args.steps
+        tf = sum(ev[s][i][0].elapsed_time(ev[s][i][1]) for s in range(k_iters)) / k_iters
+        tb = sum(ev[s][i][1].elapsed_time(ev[s][i][2]) for s in range(k_iters)) / k_iters
         kern[names[i]] = (tf, tb)
 
     # ---------------- e2e: host buffers, public class API ----------------
@@ -294,13 +334,14 @@ def run_b200(args):
 
     from adaptiveisp_b200.pipeline import GraphedHostLoop, HostStagedLoop
 
+    bank = Fm.FilterBank(flts)
+
     def isp_step(x, ft):
-        last = None
-        for f in flts:
-            y, _, _ = f(x, ft)
-            y.backward(gout)
-            last = y
-        return last
+        # all ten filters on the batch (FC layers + regressors per filter, one banked kernel set),
+        # backward through every filter's parameters; the result sent home is one output batch
+        stack, _ = bank(x, img_features=ft)
+        stack.backward(gout_all)
+        return stack[:, nf - 1].contiguous()
 
     graphed = GraphedHostLoop(lambda x, ft: isp_step(x, ft).detach(), (img, feats * 0.05), modules=flts)
 
@@ -360,6 +401,9 @@ def run_b200(args):
         pw_bytes = sum((ALGO_BYTES_FWD + ALGO_BYTES_BWD) * npx for _ in pw)
         pw_ms = sum(k["fwd_ms"] + k["bwd_ms"] for k in pw)
         step_bytes = (ALGO_BYTES_FWD + ALGO_BYTES_BWD) * npx * nf
+        # what the banked step must move through DRAM at least: the image once per direction,
+        # F outputs written, F upstream gradients read (+ the NLM d/dh stash written and read)
+        bank_min_bytes = (2 * 12 + nf * 12 + nf * 12 + 2 * 12) * npx
         line = {
             "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -379,13 +423,21 @@ def run_b200(args):
                                  "of the HBM-bound kernels are in 'kernels' / 'hbm_frac_excl_nlm'",
                          "issue_bound": nlm_issue_bound(kern["NLM"][0], npx, (clocks.samples and clk_mhz(clocks)) or 1965.0)
                          if "NLM" in kern else None},
+            "step_segments_ms": {"bank_fwd": round(seg_fwd, 4), "bank_bwd": round(seg_bwd, 4),
+                                 "unbanked_per_filter_sum": round(sum(k["fwd_ms"] + k["bwd_ms"] for k in klist), 4)},
+            # SURVEY 8(d) bytes (every filter streams its own input: 48 B per pixel-filter) over the step
+            # time; the banked step re-reads the image from L2, so its DRAM floor is bank_min_bytes
             "hbm_frac_step": step_bytes / 1e9 / (ms_max / args.steps / 1e3) / peak,
+            "dram_floor_frac_step": bank_min_bytes / 1e9 / (ms_max / args.steps / 1e3) / peak,
             "hbm_frac_excl_nlm": pw_bytes / 1e9 / (pw_ms / 1e3) / peak,
+            "kernels_note": "per-filter rows = the same kernels launched one filter at a time (unbanked), "
+                            "measured right after the timed region",
             "kernels": klist,
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps,
-                    "api": "drop-in Filter.forward + .backward() for all 10 filters, replayed as one CUDA graph per "
-                           "step by GraphedHostLoop with double-buffered pinned-host copies",
+                    "api": "FilterBank over the 10 drop-in Filter modules (their FC layers + regressors, one banked "
+                           "kernel set) + .backward(), replayed as one CUDA graph per step by GraphedHostLoop with "
+                           "double-buffered pinned-host copies",
                     "value_eager_staged": e2e_vals["staged"], "value_eager_sync": e2e_vals["sync"]},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks.summary([(tw0, tw1)] + win),

@@ -195,6 +195,30 @@ int aisp_select_apply_bwd(const float* img, const float* out, const float* grad_
                           const float* nlm_wsum, float* grad_params, float* grad_img, float* gy_scratch,
                           void* scratch, size_t scratch_bytes, void* stream);
 
+/*
+ * Filter bank: apply F filters to the SAME batch and keep every result -- the stack of
+ * agent.py:103-107 (`filtered_images.append(filter(...))` for every cfg.filter, then
+ * torch.stack(dim=1)), which is also BASELINE.json configs[1] ("all 10 filters fwd+bwd").
+ *   img     [B,3,H,W]                      out / grad_out  [B,F,3,H,W]
+ *   params  [B,F,AISP_PSTRIDE]             filter_ops      HOST array of F op codes (F <= 16,
+ *   grad_params [B,F,AISP_PSTRIDE]                         at most ONE AISP_OP_NLM, no AISP_OP_NONE)
+ *   nlm_dout_dh [B,3,H,W] device stash for the NLM slot, or NULL (forward: no stash is written;
+ *               backward: the NLM slot's grad_params row is left untouched)
+ * The kernels of aisp_select_apply_* run over "virtual samples" (v = b*F + f) whose image index
+ * is v / F; every kernel family is launched once, over its own slots only.  The F reads of an
+ * image chunk are issued by neighbouring CTAs and are served from L2 after the first, so DRAM
+ * traffic is ~(1 + F) planes forward instead of 2F.
+ * Parameter gradients only (the reference never differentiates the stack w.r.t. the input batch
+ * without going through the selection, train.py:255,341-342).  scratch_bytes >=
+ * aisp_bwd_scratch_bytes(B*F, H, W);  B*F <= 65535.
+ */
+int aisp_bank_fwd(const float* img, float* out, const float* params, const int32_t* filter_ops, int B, int F,
+                  int H, int W, int clip, float* nlm_dout_dh, void* stream);
+
+int aisp_bank_bwd(const float* img, const float* grad_out, const float* params, const int32_t* filter_ops, int B,
+                  int F, int H, int W, int clip, const float* nlm_dout_dh, float* grad_params, void* scratch,
+                  size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
