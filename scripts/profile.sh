@@ -8,8 +8,11 @@ mkdir -p $OUT
 BENCH="python bench.py --steps 2 --warmup 3 --no-cpu --no-extras"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv $BENCH > $OUT/launches_$TAG.log 2>&1
 for K in nlm_kernel sharpen_kernel pw_fwd_kernel pw_bwd_kernel; do
-  N=2; [ $K = pw_fwd_kernel ] && N=8; [ $K = pw_bwd_kernel ] && N=8
-  ncu --set full --clock-control none --import-source on -k regex:$K -s 0 -c $N -o $OUT/prof_${K}_$TAG -f $BENCH > $OUT/prof_${K}_$TAG.log 2>&1
+  # the first launches of every kernel are the banked ones (all slots of a family in one launch);
+  # PERFILTER=1 skips past warm-up + timed steps to the one-filter-at-a-time launches of the breakdown
+  N=2; S=0
+  if [ "${PERFILTER:-0}" = 1 ]; then S=5; [ $K = pw_fwd_kernel ] && N=8; [ $K = pw_bwd_kernel ] && N=8; fi
+  ncu --set full --clock-control none --import-source on -k regex:$K -s $S -c $N -o $OUT/prof_${K}_$TAG -f $BENCH > $OUT/prof_${K}_$TAG.log 2>&1
 done
 ls -la $OUT
 for K in nlm_kernel sharpen_kernel pw_fwd_kernel pw_bwd_kernel; do
