@@ -93,6 +93,22 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, c
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                   Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // torch.clip semantics: NaN stays NaN (fminf/fmaxf would swallow it)
 __device__ __forceinline__ float clip01(float y) {
     // two NaN-propagating FMNMX instead of two compare+select pairs

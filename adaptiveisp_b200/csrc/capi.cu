@@ -5,6 +5,9 @@
 namespace aisp {
 cudaError_t launch_pointwise_fwd(const float*, float*, const float*, const int32_t*, const int32_t*, int, int, int, int,
                                  int, BankMap, cudaStream_t);
+cudaError_t launch_pointwise_bank_fwd(const float*, float*, const float*, int, int, int, int, BankMap, cudaStream_t);
+cudaError_t launch_pointwise_bank_bwd(const float*, const float*, const float*, int, int, int, int, float*, float*, BankMap,
+                                      cudaStream_t);
 cudaError_t launch_pointwise_bwd(const float*, const float*, const float*, const int32_t*, int, int, int, int, float*,
                                  float*, float*, BankMap, cudaStream_t);
 cudaError_t launch_sharpen_fwd(const float*, float*, const float*, const int32_t*, int, int, int, BankMap, cudaStream_t);
@@ -209,8 +212,7 @@ int aisp_bank_fwd(const float* img, float* out, const float* params, const int32
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaSuccess;
     if (m[FAMILY_POINTWISE].n)
-        e = launch_pointwise_fwd(img, out, params, nullptr, nullptr, B * m[FAMILY_POINTWISE].n, H, W, 1, clip ? 1 : 0,
-                                 m[FAMILY_POINTWISE], st);
+        e = launch_pointwise_bank_fwd(img, out, params, B, H, W, clip ? 1 : 0, m[FAMILY_POINTWISE], st);
     if (e == cudaSuccess && m[FAMILY_SHARPEN].n)
         e = launch_sharpen_fwd(img, out, params, nullptr, B * m[FAMILY_SHARPEN].n, H, W, m[FAMILY_SHARPEN], st);
     if (e == cudaSuccess && m[FAMILY_NLM].n)
@@ -231,8 +233,8 @@ int aisp_bank_bwd(const float* img, const float* grad_out, const float* params, 
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaSuccess;
     if (m[FAMILY_POINTWISE].n)
-        e = launch_pointwise_bwd(img, grad_out, params, nullptr, B * m[FAMILY_POINTWISE].n, H, W, clip ? 1 : 0,
-                                 grad_params, nullptr, (float*)scratch, m[FAMILY_POINTWISE], st);
+        e = launch_pointwise_bank_bwd(img, grad_out, params, B, H, W, clip ? 1 : 0, grad_params, (float*)scratch,
+                                      m[FAMILY_POINTWISE], st);
     if (e == cudaSuccess && m[FAMILY_SHARPEN].n)
         e = launch_sharpen_bwd(img, grad_out, params, nullptr, B * m[FAMILY_SHARPEN].n, H, W, grad_params, nullptr,
                                nullptr, (float*)scratch, m[FAMILY_SHARPEN], st);

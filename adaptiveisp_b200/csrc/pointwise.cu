@@ -584,6 +584,66 @@ pw_fwd_kernel(const float* __restrict__ img, float* __restrict__ out, const floa
     }
 }
 
+// Filter-bank forward: CTA <-> (image, chunk).  The chunk is read ONCE into registers and every
+// per-pixel slot of the bank is applied to it in turn (op switch uniform per CTA), each result going
+// to its own plane set of the [B,F,3,H,W] stack -- per pixel 12 B read + 12 B written per slot,
+// and no reliance on L2 for the re-reads.  Arithmetic per slot is fwd_step, as in pw_fwd_kernel.
+template <int VEC>
+__global__ void __launch_bounds__(kThreads, 4)
+pw_bank_fwd_kernel(const float* __restrict__ img, float* __restrict__ out, const float* __restrict__ params, int N,
+                   int clip, BankMap bm) {
+    pdl_prologue();
+    __shared__ float raw[kMaxBankFilters][kConst];
+    __shared__ float sc[kMaxBankFilters][kConst];
+    __shared__ int sop[kMaxBankFilters];
+    __shared__ int svs[kMaxBankFilters];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = bm.n;
+    for (int j = warp; j < n; j += kWarps) {   // one warp per slot stages its row, lane 0 derives
+        const int v = bank_sample(bm, blockIdx.y * n + j);
+        raw[j][lane] = (lane < AISP_PSTRIDE) ? params[(size_t)v * AISP_PSTRIDE + lane] : 0.f;
+        sc[j][lane] = 0.f;
+        __syncwarp();
+        if (lane == 0) {
+            const int op = bank_op(bm, v);
+            sop[j] = op;
+            svs[j] = v;
+            derive_consts(op, raw[j], sc[j]);
+        }
+    }
+    __syncthreads();
+
+    constexpr int GROUPS = kPwChunkPx / (kThreads * VEC);
+    constexpr int NPX = VEC;   // one 128-bit load per plane per round: the slot loop supplies the work per load
+    const float* pr = img + (size_t)blockIdx.y * 3 * (size_t)N;
+    const int chunk0 = blockIdx.x * kPwChunkPx;
+    for (int g0 = 0; g0 < GROUPS; ++g0) {
+        const int i = chunk0 + (g0 * kThreads + threadIdx.x) * VEC;
+        if (i >= N) break;
+        Pack<VEC> xr, xg, xb;
+        xr.load(pr + i);
+        xg.load(pr + N + i);
+        xb.load(pr + 2 * (size_t)N + i);
+        for (int j = 0; j < n; ++j) {
+            float R[NPX], Gc[NPX], Bc[NPX];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { R[v] = xr.v[v]; Gc[v] = xg.v[v]; Bc[v] = xb.v[v]; }
+            fwd_step<NPX>(sop[j], sc[j], R, Gc, Bc);
+            Pack<VEC> t;
+            float* q = out + (size_t)svs[j] * 3 * (size_t)N + i;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) t.v[v] = clip ? clip01(R[v]) : R[v];
+            t.store(q);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) t.v[v] = clip ? clip01(Gc[v]) : Gc[v];
+            t.store(q + N);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) t.v[v] = clip ? clip01(Bc[v]) : Bc[v];
+            t.store(q + 2 * (size_t)N);
+        }
+    }
+}
+
 template <int OP, int VEC, bool GIMG>
 __device__ __forceinline__ void pw_bwd_body(const float* __restrict__ pr, const float* __restrict__ pg,
                                             float* __restrict__ gi, const float* c, int N, int clip,
@@ -673,6 +733,100 @@ pw_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, con
     }
 }
 
+// Filter-bank backward (parameter gradients): CTA <-> (image, chunk).  Each thread parks its own
+// pixels of the chunk in shared memory once (private slots: no barrier, conflict-free 128-bit
+// accesses) and sweeps the bank's per-pixel slots over them; only the upstream gradient of each
+// slot is streamed from HBM.  Per-thread pixel assignment, accumulation order and the block
+// reduction are those of pw_bwd_body, so the partial sums are bit-identical to F separate launches.
+template <int OP, int VEC>
+__device__ __forceinline__ void pw_bank_bwd_body(const float* __restrict__ sx, const float* __restrict__ pg,
+                                                 const float* c, int N, int clip, float* red, float* dst) {
+    constexpr int NACC = PwBwd<OP>::NACC;
+    constexpr int GROUPS = kPwChunkPx / (kThreads * VEC);
+    float acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+    const int chunk0 = blockIdx.x * kPwChunkPx;
+    for (int g0 = 0; g0 < GROUPS; ++g0) {
+        const int i = chunk0 + (g0 * kThreads + threadIdx.x) * VEC;
+        Pack<VEC> dr, dg, db;
+        float xr[VEC], xg[VEC], xb[VEC];
+        if (i < N) {
+            dr.load(pg + i); dg.load(pg + N + i); db.load(pg + 2 * (size_t)N + i);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) dr.v[v] = dg.v[v] = db.v[v] = 0.f;
+        }
+        const float* px = sx + ((size_t)(g0 * 3) * kThreads + threadIdx.x) * VEC;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            xr[v] = px[v];
+            xg[v] = px[kThreads * VEC + v];
+            xb[v] = px[2 * kThreads * VEC + v];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+            PwBwd<OP>::template px<false>(c, xr[v], xg[v], xb[v], dr.v[v], dg.v[v], db.v[v], clip, acc);
+    }
+    block_reduce_store<NACC>(acc, red, dst);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads, 4)
+pw_bank_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, const float* __restrict__ params,
+                   int N, int clip, float* __restrict__ partial, BankMap bm) {
+    pdl_prologue();
+    extern __shared__ float4 sx4[];     // [GROUPS][3][kThreads] packs of VEC floats = 3 * kPwChunkPx floats
+    float* sx = reinterpret_cast<float*>(sx4);
+    __shared__ float raw[1][kConst];
+    __shared__ float sc[1][kConst];
+    __shared__ int sop[1];
+    __shared__ float red[kWarps * AISP_ACC_STRIDE];
+    constexpr int GROUPS = kPwChunkPx / (kThreads * VEC);
+    const float* pr = img + (size_t)blockIdx.y * 3 * (size_t)N;
+    const int chunk0 = blockIdx.x * kPwChunkPx;
+#pragma unroll
+    for (int g0 = 0; g0 < GROUPS; ++g0) {
+        const int i = chunk0 + (g0 * kThreads + threadIdx.x) * VEC;
+        Pack<VEC> t[3];
+        if (i < N) {
+            t[0].load(pr + i); t[1].load(pr + N + i); t[2].load(pr + 2 * (size_t)N + i);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) t[0].v[v] = t[1].v[v] = t[2].v[v] = 0.f;
+        }
+        float* px = sx + ((size_t)(g0 * 3) * kThreads + threadIdx.x) * VEC;
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) px[pl * kThreads * VEC + v] = t[pl].v[v];
+    }
+    const int n = bm.n;
+    for (int j = 0; j < n; ++j) {
+        const int b = bank_sample(bm, blockIdx.y * n + j);
+        if (j > 0) __syncthreads();   // the previous slot's constants are no longer read
+        stage_consts(params, nullptr, b, 1, 1, raw, sc, sop, bm);
+        const float* pg = gout + (size_t)b * 3 * (size_t)N;
+        float* dst = partial + ((size_t)b * gridDim.x + blockIdx.x) * AISP_ACC_STRIDE;
+        const float* c = sc[0];
+        switch (sop[0]) {
+#define AISP_CASE(OPC) \
+    case OPC: pw_bank_bwd_body<OPC, VEC>(sx, pg, c, N, clip, red, dst); break;
+            AISP_CASE(AISP_OP_EXPOSURE)
+            AISP_CASE(AISP_OP_GAMMA)
+            AISP_CASE(AISP_OP_WB)
+            AISP_CASE(AISP_OP_CCM)
+            AISP_CASE(AISP_OP_TONE)
+            AISP_CASE(AISP_OP_COLOR)
+            AISP_CASE(AISP_OP_CONTRAST)
+            AISP_CASE(AISP_OP_WNB)
+            AISP_CASE(AISP_OP_SATPLUS)
+#undef AISP_CASE
+        default: break;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 finalize_kernel(const float* __restrict__ partial, int nrows, const float* __restrict__ params,
                 const int32_t* __restrict__ ops, int family, float* __restrict__ grad_params, BankMap bm) {
@@ -727,6 +881,18 @@ cudaError_t launch_pointwise_fwd(const float* img, float* out, const float* para
     return cudaGetLastError();
 }
 
+// bank forward over the per-pixel slots of `bm` (bm.n >= 1): grid (chunks, images)
+cudaError_t launch_pointwise_bank_fwd(const float* img, float* out, const float* params, int B, int H, int W, int clip,
+                                      BankMap bm, cudaStream_t st) {
+    const long long N = (long long)H * W;
+    dim3 grid((unsigned)((N + kPwChunkPx - 1) / kPwChunkPx), (unsigned)B);
+    if ((N % 4 == 0) && aligned16(img) && aligned16(out))
+        launch_pdl(pw_bank_fwd_kernel<4>, grid, kThreads, st, img, out, params, (int)N, clip, bm);
+    else
+        launch_pdl(pw_bank_fwd_kernel<1>, grid, kThreads, st, img, out, params, (int)N, clip, bm);
+    return cudaGetLastError();
+}
+
 int pointwise_rows(int H, int W) { return (int)(((long long)H * W + kPwChunkPx - 1) / kPwChunkPx); }
 
 cudaError_t launch_finalize(const float* partial, int nrows, const float* params, const int32_t* ops, int family,
@@ -756,6 +922,30 @@ cudaError_t launch_pointwise_bwd(const float* img, const float* gout, const floa
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return launch_finalize(partial, rows, params, ops, FAMILY_POINTWISE, B, grad_params, bm, st);
+}
+
+// bank backward over the per-pixel slots of `bm` (bm.n >= 1): grid (chunks, images) + finalize
+cudaError_t launch_pointwise_bank_bwd(const float* img, const float* gout, const float* params, int B, int H, int W,
+                                      int clip, float* grad_params, float* partial, BankMap bm, cudaStream_t st) {
+    const long long N = (long long)H * W;
+    const int rows = pointwise_rows(H, W);
+    dim3 grid((unsigned)rows, (unsigned)B);
+    constexpr size_t smem = 3 * kPwChunkPx * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {   // > 48 KB of dynamic shared memory is opt-in (per function, idempotent)
+        cudaFuncSetAttribute(pw_bank_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(pw_bank_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(pw_bank_bwd_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(pw_bank_bwd_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_set = true;
+    }
+    if ((N % 4 == 0) && aligned16(img) && aligned16(gout))
+        launch_pdl_smem(pw_bank_bwd_kernel<4>, grid, kThreads, smem, st, img, gout, params, (int)N, clip, partial, bm);
+    else
+        launch_pdl_smem(pw_bank_bwd_kernel<1>, grid, kThreads, smem, st, img, gout, params, (int)N, clip, partial, bm);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return launch_finalize(partial, rows, params, nullptr, FAMILY_POINTWISE, B * bm.n, grad_params, bm, st);
 }
 
 // =============================================================================================

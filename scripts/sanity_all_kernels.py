@@ -26,6 +26,11 @@ for (B, H, W) in [(3, 37, 53), (2, 48, 64), (1, 9, 130)]:
     Pq = P.clone().requires_grad_(True)
     y = AF.apply_ops(x, Pq, ops, True)
     (y * g).sum().backward()
+    # filter bank: all 13 ops on the same batch (fused per-pixel bank kernels, compact grids)
+    bank_ops = list(range(13))
+    Pb = (torch.rand((B, 13, 24), device=dev) * 0.5 + 0.6).requires_grad_(True)
+    yb = AF.apply_bank(img, Pb, bank_ops, clip=True)
+    (yb * torch.randn_like(yb)).sum().backward()
     steps = [[0, 1, 3, 9, 4][: 1 + b % 5] for b in range(B)]
     params = [[torch.rand(AF.NUM_PARAMS[o]) * 0.5 + 0.5 for o in s] for s in steps]
     out = replay.execute_plan(img, replay.plan_pipeline(steps, params, dev), True)
