@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import c_char_p, c_int, c_size_t, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_size_t, c_void_p
 
 import torch
 
@@ -42,6 +42,9 @@ SIGNATURES = {
     "aisp_select_apply_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "aisp_select_apply_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_size_t,
                                       _P]),
+    "aisp_select": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P,
+                            _P, _P]),
+    "aisp_select_bwd": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "aisp_bank_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "aisp_bank_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
 }

@@ -122,8 +122,9 @@ class Agent(nn.Module):
             rows.append(AF.pack_params(p, flt.get_num_filter_parameters()))
         return torch.stack(rows, dim=1), per_filter
 
-    def select(self, x_down, states, selection_noise, selected_filter_id=None):
-        """agent.py:119-149 -> (pdf, entropy[B,1], selected int64 [B], one_hot int64 [B,F])."""
+    def policy(self, x_down, states):
+        """agent.py:119-133 -> (pdf [B,F] with the exploration mix, entropy [B,1]); stays PyTorch
+        (the policy gradient flows through both)."""
         n = len(self.filters)
         feats = self.action_selection(enrich_image_input(self.cfg, x_down, states))
         feats = self.lrelu(self.fc1(feats))
@@ -131,6 +132,13 @@ class Agent(nn.Module):
         pdf = pdf * (1 - self.cfg.exploration) + self.cfg.exploration * 1.0 / n
         pdf = pdf / (torch.sum(pdf, dim=1, keepdim=True) + 1e-30)
         entropy = torch.sum(-pdf * torch.log(pdf), dim=1)[:, None]
+        return pdf, entropy
+
+    def select(self, x_down, states, selection_noise, selected_filter_id=None):
+        """agent.py:119-149 -> (pdf, entropy[B,1], selected int64 [B], one_hot int64 [B,F]) as PyTorch
+        ops (kept as the readable statement of the selection; ``forward`` runs ``aisp_select``)."""
+        n = len(self.filters)
+        pdf, entropy = self.policy(x_down, states)
         if selected_filter_id is not None:
             sel = torch.full((pdf.shape[0],), int(selected_filter_id), dtype=torch.int64, device=pdf.device)
         elif self.training:
@@ -157,11 +165,19 @@ class Agent(nn.Module):
             raise ValueError("current just support shared_feature_extractor")
         filter_features = self.feature_extractor(enrich_image_input(self.cfg, x_down, states))
         packed_all, per_filter = self.predict_all_params(filter_features)
-        pdf, entropy, sel, hot = self.select(x_down, states, selection_noise, selected_filter_id)
+        pdf, entropy = self.policy(x_down, states)
+        # selection, one-hot, parameter-row gather and the state update: ONE launch, no host sync
+        if selected_filter_id is not None:
+            mode, forced = AF.SELECT_FORCED, int(selected_filter_id)
+        else:
+            mode, forced = (AF.SELECT_SAMPLE if self.training else AF.SELECT_ARGMAX), 0
+        rows, sel, hot, ops, new_states, pens = AF.select_rows(
+            pdf, selection_noise, states.to(torch.float32), packed_all, self._op_table.to(x.device), mode, forced,
+            float(self.cfg.test_steps), float(self.cfg.early_stop_penalty))
         surrogate = torch.sum(hot * torch.log(pdf + 1e-10), dim=1, keepdim=True)
 
         x_in = x
-        x, rows, ops = self.apply_selected(x_in, packed_all, sel)
+        x = AF.apply_ops(x_in, rows, ops, clip=True, family=None)
         high_res_output = None
         if high_res is not None:
             high_res_output = AF.apply_ops(high_res, rows, ops, clip=True, family=None)
@@ -186,15 +202,8 @@ class Agent(nn.Module):
 
         debugger.width = int(x.shape[2])
 
-        # new states (agent.py:234-259)
-        hot_f = hot.to(states.dtype)
-        is_last = (torch.abs(states[:, STATE_STEP_DIM:STATE_STEP_DIM + 1] + 1 - self.cfg.test_steps) < 1e-4) \
-            .to(torch.float32)
-        step = (states[:, STATE_STEP_DIM] + 1)[:, None]
-        usage = states[:, STATE_STEP_DIM + 1:]
-        early_stop_penalty = (1 - is_last) * is_last * self.cfg.early_stop_penalty
-        usage_penalty = torch.sum(usage * hot, dim=1, keepdim=True)
-        new_states = torch.cat([is_last, is_last, step, torch.maximum(usage, hot_f)], dim=1)
+        # new states and the two state-dependent penalties (agent.py:234-259) came out of aisp_select
+        usage_penalty, early_stop_penalty = pens[:, 0:1], pens[:, 1:2]
 
         if self.cfg.clamp:
             x = torch.clip(x, min=0.0, max=5.0)

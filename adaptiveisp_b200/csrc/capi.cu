@@ -22,6 +22,9 @@ cudaError_t launch_nlm_bwd(const float*, const float*, const float*, const int32
 cudaError_t launch_block_mean(const float*, float*, int, int, int, int, int, cudaStream_t);
 cudaError_t launch_pointwise_chain_bwd(const float*, const float*, const float*, const int32_t*, const int32_t*, int, int,
                                        int, int, int, float*, float*, float*, cudaStream_t);
+cudaError_t launch_select(const float*, const float*, int, int, const float*, const float*, const int32_t*, int, int, int,
+                          float, float, long long*, long long*, int32_t*, float*, float*, float*, cudaStream_t);
+cudaError_t launch_select_bwd(const float*, const long long*, int, int, float*, cudaStream_t);
 int chain_bwd_max_steps();
 int pointwise_rows(int H, int W);
 int sharpen_rows(int H, int W);
@@ -179,6 +182,28 @@ int aisp_select_apply_bwd(const float* img, const float* out, const float* grad_
     if (e) return e;
     if (grad_img) e = aisp_nlm_bwd_img(img, out, nlm_wsum, grad_out, params, ops, B, H, W, grad_img, stream);
     return e;
+}
+
+int aisp_select(const float* pdf, const float* noise, int mode, int forced_id, const float* states,
+                const float* packed_all, const int32_t* op_table, int B, int F, int S, float test_steps,
+                float early_stop_penalty, int64_t* sel, int64_t* one_hot, int32_t* ops, float* rows, float* new_states,
+                float* penalties, void* stream) {
+    if (!pdf || !states || !packed_all || !op_table || !sel || !one_hot || !ops || !rows || !new_states || !penalties)
+        return AISP_ERR_NULL;
+    if (mode == AISP_SELECT_SAMPLE && !noise) return AISP_ERR_NULL;
+    if (B <= 0 || F <= 0 || S != 3 + F || (long long)B * F * AISP_PSTRIDE > (1LL << 30)) return AISP_ERR_SHAPE;
+    if (mode < AISP_SELECT_SAMPLE || mode > AISP_SELECT_FORCED) return AISP_ERR_UNSUPPORTED;
+    if (mode == AISP_SELECT_FORCED && (forced_id < 0 || forced_id >= F)) return AISP_ERR_SHAPE;
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+    return (int)launch_select(pdf, noise, mode, forced_id, states, packed_all, op_table, B, F, S, test_steps,
+                              early_stop_penalty, (long long*)sel, (long long*)one_hot, ops, rows, new_states,
+                              penalties, (cudaStream_t)stream);
+}
+
+int aisp_select_bwd(const float* grad_rows, const int64_t* sel, int B, int F, float* grad_packed_all, void* stream) {
+    if (!grad_rows || !sel || !grad_packed_all) return AISP_ERR_NULL;
+    if (B <= 0 || F <= 0 || (long long)B * F * AISP_PSTRIDE > (1LL << 30)) return AISP_ERR_SHAPE;
+    return (int)launch_select_bwd(grad_rows, (const long long*)sel, B, F, grad_packed_all, (cudaStream_t)stream);
 }
 
 // ---- filter bank: F filters applied to the SAME batch (agent.py:103-107 runs every cfg.filter on

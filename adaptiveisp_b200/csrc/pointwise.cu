@@ -931,7 +931,10 @@ cudaError_t launch_pointwise_bank_bwd(const float* img, const float* gout, const
     const int rows = pointwise_rows(H, W);
     dim3 grid((unsigned)rows, (unsigned)B);
     constexpr size_t smem = 3 * kPwChunkPx * sizeof(float);
-    static bool attr_set = false;
+    static bool attr_set_on[64] = {};   // per device: function attributes belong to the device's context
+    int devi = 0;
+    cudaGetDevice(&devi);
+    bool& attr_set = attr_set_on[devi & 63];
     if (!attr_set) {   // > 48 KB of dynamic shared memory is opt-in (per function, idempotent)
         cudaFuncSetAttribute(pw_bank_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(pw_bank_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

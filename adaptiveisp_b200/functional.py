@@ -217,6 +217,70 @@ def apply_bank(img: torch.Tensor, P: torch.Tensor, ops: Sequence[int], clip: boo
     return _ApplyBank.apply(img, P.contiguous(), ops, clip)
 
 
+SELECT_SAMPLE, SELECT_ARGMAX, SELECT_FORCED = 0, 1, 2   # enum aisp_select_mode
+
+
+class _SelectRows(torch.autograd.Function):
+    """Selection + one-hot + parameter-row gather + state update in one launch (``aisp_select``).
+    Differentiable w.r.t. ``packed_all`` only (the gather); everything else is integer bookkeeping."""
+
+    @staticmethod
+    def forward(ctx, pdf, noise, states, packed_all, op_table, mode: int, forced: int, test_steps: float,
+                early_stop_c: float):
+        B, F = pdf.shape
+        S = states.shape[1]
+        dev = pdf.device
+        for name, t in (("pdf", pdf), ("states", states), ("packed_all", packed_all)):
+            if not t.is_cuda or t.dtype != torch.float32:
+                raise _lib.AispError(f"{name} must be a CUDA float32 tensor")
+        if packed_all.shape != (B, F, PSTRIDE) or S != 3 + F or op_table.numel() != F:
+            raise _lib.AispError("select: expected pdf [B,F], states [B,3+F], packed_all [B,F,24], op_table [F]")
+        pdf, states, packed_all = pdf.contiguous(), states.contiguous(), packed_all.contiguous()
+        if noise is not None:
+            noise = noise.reshape(B).to(torch.float32).contiguous()
+        sel = torch.empty((B,), dtype=torch.int64, device=dev)
+        hot = torch.empty((B, F), dtype=torch.int64, device=dev)
+        ops = torch.empty((B,), dtype=torch.int32, device=dev)
+        rows = torch.empty((B, PSTRIDE), dtype=torch.float32, device=dev)
+        new_states = torch.empty((B, S), dtype=torch.float32, device=dev)
+        pens = torch.empty((B, 2), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().aisp_select(pdf.data_ptr(), _lib.ptr(noise), int(mode), int(forced), states.data_ptr(),
+                                        packed_all.data_ptr(), op_table.data_ptr(), B, F, S, float(test_steps),
+                                        float(early_stop_c), sel.data_ptr(), hot.data_ptr(), ops.data_ptr(),
+                                        rows.data_ptr(), new_states.data_ptr(), pens.data_ptr(), _lib.stream_ptr(dev))
+        _lib.check(rc, "aisp_select")
+        ctx.save_for_backward(sel)
+        ctx.F = F
+        ctx.mark_non_differentiable(sel, hot, ops, new_states, pens)
+        return rows, sel, hot, ops, new_states, pens
+
+    @staticmethod
+    def backward(ctx, g_rows, *_):
+        (sel,) = ctx.saved_tensors
+        if not ctx.needs_input_grad[3]:
+            return (None,) * 9
+        B, F = sel.shape[0], ctx.F
+        g_rows = g_rows.contiguous()
+        g_all = torch.empty((B, F, PSTRIDE), dtype=torch.float32, device=sel.device)
+        with torch.cuda.device(sel.device):
+            rc = _lib.lib().aisp_select_bwd(g_rows.data_ptr(), sel.data_ptr(), B, F, g_all.data_ptr(),
+                                            _lib.stream_ptr(sel.device))
+        _lib.check(rc, "aisp_select_bwd")
+        return None, None, None, g_all, None, None, None, None, None
+
+
+def select_rows(pdf, noise, states, packed_all, op_table, mode: int, forced: int = 0, test_steps: float = 5.0,
+                early_stop_c: float = 1.0):
+    """Device-side selection step (agent.py:12-23,126-154,234-259) -> ``(rows [B,24], sel [B] int64,
+    one_hot [B,F] int64, ops [B] int32, new_states [B,S], penalties [B,2] = (usage, early stop))``.
+    ``mode``: ``SELECT_SAMPLE`` (training, needs ``noise`` [B] or [B,1]), ``SELECT_ARGMAX`` (eval) or
+    ``SELECT_FORCED`` (``forced`` = filter index).  ``pdf`` is read as data (no gradient through the
+    integer choice); ``rows`` carries the gradient back to ``packed_all``."""
+    return _SelectRows.apply(pdf.detach(), noise, states.detach(), packed_all, op_table, mode, forced, test_steps,
+                             early_stop_c)
+
+
 class _ApplyChain(torch.autograd.Function):
     """Per-sample sequences of per-pixel filters, forward AND backward each fused into one pass."""
 

@@ -196,6 +196,33 @@ int aisp_select_apply_bwd(const float* img, const float* out, const float* grad_
                           void* scratch, size_t scratch_bytes, void* stream);
 
 /*
+ * Device-side filter selection + agent-state update in one launch, no host round trip:
+ * pdf_sample / argmax / forced id (agent.py:12-16,126-149), one_hot (agent.py:18-23), the gather
+ * of the selected filter's parameter row (the B200 form of agent.py:154: pick the row before the
+ * filter runs instead of one of ten images after) and the new state (agent.py:234-259).
+ *   pdf        [B,F]   selection probabilities (after the exploration mix and renormalisation)
+ *   noise      [B]     uniform noise z[:,0] (AISP_SELECT_SAMPLE only, else may be NULL)
+ *   states     [B,S]   S = 3 + F: (reward, stopped, step, usage[F])            (util.py:15-18)
+ *   packed_all [B,F,AISP_PSTRIDE]  every filter's packed parameter row
+ *   op_table   [F]     int32, filter index -> aisp_op (device)
+ * outputs: sel [B] int64 (-1 possible: pdf_sample with noise == 0), one_hot [B,F] int64,
+ *   ops [B] int32 (AISP_OP_NONE for sel == -1), rows [B,AISP_PSTRIDE] (zeros for sel == -1),
+ *   new_states [B,S], penalties [B,2] = (usage penalty, early-stop penalty).
+ * Sums are sequential fp32 in index order, like torch.cumsum / torch.sum over a 10-entry row.
+ */
+enum aisp_select_mode { AISP_SELECT_SAMPLE = 0, AISP_SELECT_ARGMAX = 1, AISP_SELECT_FORCED = 2 };
+
+int aisp_select(const float* pdf, const float* noise, int mode, int forced_id, const float* states,
+                const float* packed_all, const int32_t* op_table, int B, int F, int S, float test_steps,
+                float early_stop_penalty, int64_t* sel, int64_t* one_hot, int32_t* ops, float* rows,
+                float* new_states, float* penalties, void* stream);
+
+/* Backward of the row gather: grad_packed_all [B,F,AISP_PSTRIDE] = grad_rows scattered to the
+ * selected slot, exact zeros elsewhere (what torch.gather's backward gives the reference). */
+int aisp_select_bwd(const float* grad_rows, const int64_t* sel, int B, int F, float* grad_packed_all,
+                    void* stream);
+
+/*
  * Filter bank: apply F filters to the SAME batch and keep every result -- the stack of
  * agent.py:103-107 (`filtered_images.append(filter(...))` for every cfg.filter, then
  * torch.stack(dim=1)), which is also BASELINE.json configs[1] ("all 10 filters fwd+bwd").

@@ -31,6 +31,15 @@ for (B, H, W) in [(3, 37, 53), (2, 48, 64), (1, 9, 130)]:
     Pb = (torch.rand((B, 13, 24), device=dev) * 0.5 + 0.6).requires_grad_(True)
     yb = AF.apply_bank(img, Pb, bank_ops, clip=True)
     (yb * torch.randn_like(yb)).sum().backward()
+    # device-side selection (all three modes) + the row-gather backward
+    Fsel = 10
+    pdf = torch.softmax(torch.randn((B, Fsel), device=dev), dim=1)
+    st = torch.zeros((B, 3 + Fsel), device=dev)
+    tab = torch.arange(Fsel, dtype=torch.int32, device=dev)
+    for mode in (AF.SELECT_SAMPLE, AF.SELECT_ARGMAX, AF.SELECT_FORCED):
+        pk = torch.randn((B, Fsel, 24), device=dev, requires_grad=True)
+        rows = AF.select_rows(pdf, torch.rand((B, 1), device=dev), st, pk, tab, mode, 3)[0]
+        rows.sum().backward()
     steps = [[0, 1, 3, 9, 4][: 1 + b % 5] for b in range(B)]
     params = [[torch.rand(AF.NUM_PARAMS[o]) * 0.5 + 0.5 for o in s] for s in steps]
     out = replay.execute_plan(img, replay.plan_pipeline(steps, params, dev), True)

@@ -94,6 +94,55 @@ int main(void) {
     for (int i = 3 * N; i < n; ++i)
         if (fabsf(h_out[i] - 0.25f) > 1e-6f) return fail("nlm constant image", h_out[i], 0.25);
 
+    /* 3b. filter bank: {exposure 0 EV, white balance (1,1,1), 3x3 sharpen factor 1} on the same batch
+     *     -> a [B,3,3,H,W] stack of three copies of the image; the backward of the exposure slot with
+     *     g = 1 is ln2 * sum(x) again, the two other slots receive their own rows */
+    {
+        const int F = 3;
+        const int32_t fops[3] = {AISP_OP_EXPOSURE, AISP_OP_WB, AISP_OP_SHARPEN};   /* HOST array */
+        float bpar[2 * 3 * AISP_PSTRIDE];
+        float *d_stack, *d_gstack, *d_bpar, *d_bgp;
+        void* d_bscr;
+        size_t bscr = aisp_bwd_scratch_bytes(B * F, H, W);
+        memset(bpar, 0, sizeof(bpar));
+        for (int b = 0; b < B; ++b) {
+            bpar[(b * F + 1) * AISP_PSTRIDE + 0] = bpar[(b * F + 1) * AISP_PSTRIDE + 1] = bpar[(b * F + 1) * AISP_PSTRIDE + 2] = 1.0f;
+            bpar[(b * F + 2) * AISP_PSTRIDE] = 1.0f;
+        }
+        CK(cudaMalloc((void**)&d_stack, sizeof(float) * n * F));
+        CK(cudaMalloc((void**)&d_gstack, sizeof(float) * n * F));
+        CK(cudaMalloc((void**)&d_bpar, sizeof(bpar)));
+        CK(cudaMalloc((void**)&d_bgp, sizeof(bpar)));
+        CK(cudaMalloc(&d_bscr, bscr));
+        CK(cudaMemcpy(d_bpar, bpar, sizeof(bpar), cudaMemcpyHostToDevice));
+        float* h_stack = malloc(sizeof(float) * n * F);
+        for (int i = 0; i < n * F; ++i) h_stack[i] = 1.0f;
+        CK(cudaMemcpy(d_gstack, h_stack, sizeof(float) * n * F, cudaMemcpyHostToDevice));
+        CK(aisp_bank_fwd(d_img, d_stack, d_bpar, fops, B, F, H, W, 0, NULL, NULL));
+        CK(aisp_bank_bwd(d_img, d_gstack, d_bpar, fops, B, F, H, W, 0, NULL, d_bgp, d_bscr, bscr, NULL));
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(h_stack, d_stack, sizeof(float) * n * F, cudaMemcpyDeviceToHost));
+        for (int b = 0; b < B; ++b)
+            for (int f = 0; f < F; ++f)
+                for (int i = 0; i < 3 * N; ++i) {
+                    const float want = h_img[b * 3 * N + i];
+                    const float got = h_stack[((size_t)(b * F + f) * 3) * N + i];
+                    /* the reference's WB divides by (1e-5 + 0.27+0.67+0.06) */
+                    if (fabsf(got - want) > 2e-5f) return fail("bank identity stack", got, want);
+                }
+        float bgp[2 * 3 * AISP_PSTRIDE];
+        CK(cudaMemcpy(bgp, d_bgp, sizeof(bgp), cudaMemcpyDeviceToHost));
+        for (int b = 0; b < B; ++b) {
+            double s = 0;
+            for (int i = 0; i < 3 * N; ++i) s += h_img[b * 3 * N + i];
+            if (fabs(bgp[(b * F) * AISP_PSTRIDE] - s * 0.6931471805599453) > 1e-4 * s)
+                return fail("bank exposure grad", bgp[(b * F) * AISP_PSTRIDE], s * 0.693147);
+        }
+        const int32_t two_nlm[2] = {AISP_OP_NLM, AISP_OP_NLM};
+        if (aisp_bank_fwd(d_img, d_stack, d_bpar, two_nlm, B, 2, H, W, 0, NULL, NULL) != AISP_ERR_UNSUPPORTED)
+            return fail("bank: two NLM slots must be refused", 0, 0);
+    }
+
     /* 4. argument errors come back as negative status codes, not crashes */
     if (aisp_pointwise_fwd(NULL, d_out, d_par, d_ops, NULL, B, H, W, 1, 0, NULL) != AISP_ERR_NULL) return fail("null check", 0, 0);
     if (aisp_pointwise_fwd(d_img, d_img, d_par, d_ops, NULL, B, H, W, 1, 0, NULL) != AISP_ERR_UNSUPPORTED) return fail("alias check", 0, 0);
