@@ -80,6 +80,56 @@ def test_pack_params_layouts():
         assert float(row[:, O.OP_NPARAMS[op]:].abs().sum()) == 0.0
 
 
+def test_bank_and_select_argument_validation(lib):
+    """The bank's op list is a HOST array: everything about it is decided before the first launch."""
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.addressof(buf)
+    I32 = ctypes.c_int32
+    ok3 = (I32 * 3)(O.OP_EXPOSURE, O.OP_NLM, O.OP_SHARPEN)
+    assert lib.aisp_bank_fwd(None, p, p, ok3, 1, 3, 8, 8, 1, None, None) == -1
+    assert lib.aisp_bank_fwd(p, p + 4, p, None, 1, 3, 8, 8, 1, None, None) == -1
+    assert lib.aisp_bank_fwd(p, p, p, ok3, 1, 3, 8, 8, 1, None, None) == -4                    # in place
+    assert lib.aisp_bank_fwd(p, p + 4, p, ok3, 1, 0, 8, 8, 1, None, None) == -2                # F < 1
+    assert lib.aisp_bank_fwd(p, p + 4, p, (I32 * 17)(*[0] * 17), 1, 17, 8, 8, 1, None, None) == -2   # F > 16
+    assert lib.aisp_bank_fwd(p, p + 4, p, ok3, 30000, 3, 8, 8, 1, None, None) == -2            # B*F > 65535
+    two_nlm = (I32 * 2)(O.OP_NLM, O.OP_NLM)
+    assert lib.aisp_bank_fwd(p, p + 4, p, two_nlm, 1, 2, 8, 8, 1, None, None) == -4            # one stash per image
+    assert lib.aisp_bank_fwd(p, p + 4, p, (I32 * 1)(-1), 1, 1, 8, 8, 1, None, None) == -4      # NONE is not a slot
+    assert lib.aisp_bank_fwd(p, p + 4, p, (I32 * 1)(13), 1, 1, 8, 8, 1, None, None) == -4
+    assert lib.aisp_bank_bwd(p, p, p, ok3, 1, 3, 8, 8, 1, None, p, p, 4, None) == -3           # scratch for B*F samples
+    assert lib.aisp_bwd_scratch_bytes(64 * 10, 512, 512) == 10 * lib.aisp_bwd_scratch_bytes(64, 512, 512)
+    # aisp_select: S must be 3 + F, sampling needs the noise, forced ids must name a filter
+    i64 = ctypes.addressof((ctypes.c_int64 * 64)())
+    args = lambda noise, mode, forced, S: (p, noise, mode, forced, p, p, p, 2, 10, S, 5.0, 1.0, i64, i64, p, p, p, p, None)
+    assert lib.aisp_select(*args(None, 0, 0, 13)) == -1
+    assert lib.aisp_select(*args(p, 0, 0, 12)) == -2
+    assert lib.aisp_select(*args(p, 3, 0, 13)) == -4
+    assert lib.aisp_select(*args(None, 2, 10, 13)) == -2
+    assert lib.aisp_select_bwd(None, i64, 2, 10, p, None) == -1
+
+
+def test_filter_bank_host_side():
+    """FilterBank is a view over already built modules: op list in cfg.filters order, parameters
+    regressed per filter in the reference's layouts (no kernel call here)."""
+    from adaptiveisp_b200 import filters
+    from adaptiveisp_b200.config import make_cfg
+    cfg = make_cfg()
+    mods = [c(cfg, predict=True) for c in cfg.filters]
+    bank = filters.FilterBank(mods)
+    assert bank.ops == [O.OP_EXPOSURE, O.OP_GAMMA, O.OP_CCM, O.OP_SHARPEN, O.OP_NLM, O.OP_TONE, O.OP_CONTRAST,
+                        O.OP_SATPLUS, O.OP_WNB, O.OP_WB]
+    feats = torch.randn(3, cfg.feature_extractor_dims)
+    params = bank.parameters_for(img_features=feats)
+    for m, prm in zip(mods, params):
+        assert prm.shape[0] == 3 and prm[0].numel() == m.get_num_filter_parameters()
+        assert torch.equal(prm, m.filter_param_regressor(m.extract_parameters(feats)[0]))
+    assert bank.parameters_for(specified_parameters=params) == params
+    with pytest.raises(ValueError):
+        filters.FilterBank([])
+    with pytest.raises(Exception, match="no CPU path|CUDA"):
+        bank(torch.zeros((3, 3, 8, 8)), img_features=feats)
+
+
 def test_cpu_tensors_are_rejected_not_converted():
     from adaptiveisp_b200 import AispError, filters
     from adaptiveisp_b200.config import make_cfg
