@@ -360,7 +360,7 @@ class FilterBank:
         stack = torch.stack([f(img, img_features)[0] for f in filters], dim=1)      # [B,F,3,H,W]
 
     but the image arithmetic of all F filters is three kernel launches (``functional.apply_bank``)
-    instead of F, and the F reads of the image share L2.  Parameter regression stays per filter
+    instead of F, and the image is fetched from HBM once.  Parameter regression stays per filter
     (the FC layers differ); ``filters`` are the already constructed drop-in modules, so their
     weights / ``state_dict`` are untouched.  Not an ``nn.Module``: it owns no parameters.
     """

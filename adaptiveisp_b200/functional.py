@@ -197,7 +197,8 @@ class _ApplyBank(torch.autograd.Function):
 def apply_bank(img: torch.Tensor, P: torch.Tensor, ops: Sequence[int], clip: bool = True) -> torch.Tensor:
     """All of ``ops`` (F op codes) applied to the same batch, results stacked on dim 1 -- the
     ``torch.stack([f(img, ...) for f in filters], dim=1)`` of agent.py:103-107 -- in three launches
-    (one per kernel family) whose F reads of every image chunk share L2.
+    (one per kernel family): the image is fetched from HBM once per direction, not once per filter,
+    and the values are bit-identical to F separate :func:`apply_ops` calls.
 
     img ``[B,3,H,W]`` (no gradient flows to it); P ``[B,F,PSTRIDE]`` packed rows (may require grad);
     returns ``[B,F,3,H,W]``.  At most one NLM entry in ``ops`` (its d/dh stash is kept compact).

@@ -231,10 +231,11 @@ int aisp_select_bwd(const float* grad_rows, const int64_t* sel, int B, int F, fl
  *   grad_params [B,F,AISP_PSTRIDE]                         at most ONE AISP_OP_NLM, no AISP_OP_NONE)
  *   nlm_dout_dh [B,3,H,W] device stash for the NLM slot, or NULL (forward: no stash is written;
  *               backward: the NLM slot's grad_params row is left untouched)
- * The kernels of aisp_select_apply_* run over "virtual samples" (v = b*F + f) whose image index
- * is v / F; every kernel family is launched once, over its own slots only.  The F reads of an
- * image chunk are issued by neighbouring CTAs and are served from L2 after the first, so DRAM
- * traffic is ~(1 + F) planes forward instead of 2F.
+ * Every kernel family is launched once, over its own slots only ("virtual samples" v = b*F + f,
+ * image index v / F).  The per-pixel slots of an image chunk are all applied by the same CTA (the
+ * chunk is read once: into registers forward, into a shared-memory cache backward); the stencil
+ * slots share the image through L2.  DRAM traffic is ~(1 + F) planes forward instead of 2F.
+ * Results are bit-identical to F separate aisp_select_apply_* calls.
  * Parameter gradients only (the reference never differentiates the stack w.r.t. the input batch
  * without going through the selection, train.py:255,341-342).  scratch_bytes >=
  * aisp_bwd_scratch_bytes(B*F, H, W);  B*F <= 65535.
