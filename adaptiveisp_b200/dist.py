@@ -52,3 +52,52 @@ def allreduce_grads(params: Iterable[torch.nn.Parameter], average: bool = True, 
         g.copy_(flat[off:off + n].view_as(g))
         off += n
     return flat.numel() * flat.element_size()
+
+
+# ---------------------------------------------------------------------------------------------
+# NUMA placement of a rank's pinned host buffers.
+# With one process per GPU every rank streams ~400 MB per step through pinned host memory
+# (train.py:255, :378-381).  Pinned pages land on the NUMA node of the allocating thread; if that
+# is not the node the GPU's PCIe root hangs off, every copy crosses the socket interconnect and the
+# ranks of a node contend for it.  Pinning the process to the GPU's node before the buffers are
+# allocated keeps each rank's traffic on its own memory controllers.
+# ---------------------------------------------------------------------------------------------
+def gpu_numa_node(device_index: int) -> int:
+    """NUMA node of the GPU's PCIe function from sysfs, or -1 when unknown (single-node hosts, VMs)."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            return int(f.read().strip())
+    except Exception:
+        return -1
+
+
+def _parse_cpulist(text: str) -> List[int]:
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int):
+    """Restrict this process to the CPUs of the GPU's NUMA node (so that pinned buffers allocated
+    afterwards are node-local).  Returns ``(node, previous_affinity)``; ``node == -1`` means nothing
+    was changed.  Undo with ``os.sched_setaffinity(0, previous_affinity)``."""
+    import os
+    prev = os.sched_getaffinity(0)
+    node = gpu_numa_node(device_index)
+    if node < 0:
+        return -1, prev
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set(_parse_cpulist(f.read())) & prev
+        if not cpus:
+            return -1, prev
+        os.sched_setaffinity(0, cpus)
+        return node, prev
+    except Exception:
+        return -1, prev

@@ -324,6 +324,9 @@ def run_b200(args):
         kern[names[i]] = (tf, tb)
 
     # ---------------- e2e: host buffers, public class API ----------------
+    # pinned buffers on the GPU's own NUMA node (first touch by a thread bound to it)
+    from adaptiveisp_b200.dist import bind_to_gpu_numa_node
+    numa_node, prev_affinity = bind_to_gpu_numa_node(local) if not args.no_numa else (-1, None)
     host_img = torch.empty(img.shape, dtype=torch.float32, pin_memory=True)
     host_img.copy_(img.cpu())
     host_out = torch.empty(img.shape, dtype=torch.float32, pin_memory=True)
@@ -331,6 +334,8 @@ def run_b200(args):
     host_feat.copy_((feats * 0.05).cpu())
     for f in flts:
         f.train()
+    if numa_node >= 0:
+        os.sched_setaffinity(0, prev_affinity)     # the launch thread and the CPU baseline may use every core
 
     from adaptiveisp_b200.pipeline import GraphedHostLoop, HostStagedLoop
 
@@ -434,7 +439,7 @@ def run_b200(args):
                             "measured right after the timed region",
             "kernels": klist,
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps,
+                    "steps": e2e_steps, "pinned_numa_node": numa_node,
                     "api": "FilterBank over the 10 drop-in Filter modules (their FC layers + regressors, one banked "
                            "kernel set) + .backward(), replayed as one CUDA graph per step by GraphedHostLoop with "
                            "double-buffered pinned-host copies",
@@ -597,6 +602,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary configurations")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the pinned host buffers to the GPU's NUMA node")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
