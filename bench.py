@@ -591,6 +591,59 @@ def extras(dev, L, peak):
     out["config5_hetero_b256"] = {"ms_fwd": round(ms, 3), "filter_applications": napp, "phases": len(plan.phases),
                                   "launches": plan.launches, "MP_s_fwd": round(napp * H * W / 1e6 / (ms / 1e3), 1),
                                   "nlm_applications": sum(s.count(AF.OP_NLM) for s in steps)}
+    del img
+    # (d) configs[2]-style rollout, ISP side only (the detector / critic stay PyTorch and are out of
+    #     scope): 8 x 512x512 frames, 5 consecutive Agent steps with the state carried, as in
+    #     yolov3/val_adaptiveisp.py:288-309 (eval: argmax selection, forward only) and as 5 training
+    #     iterations on the same images (train.py:234-381: sampled selection, forward + backward).
+    #     Device-side selection (aisp_select) leaves no host decision in the loop, so the whole
+    #     5-step rollout is ONE CUDA graph.
+    from adaptiveisp_b200.agent import Agent
+    from adaptiveisp_b200.pipeline import GraphedStep
+    B3 = 8
+    agent = Agent(cfg, shape=(16, 64, 64), device=dev).to(dev)
+    x0 = lod_batch(B3, H, W, seed=1236, device=dev)
+    z = torch.rand((B3, cfg.z_dim), device=dev)
+    s0 = torch.zeros((B3, cfg.num_state_dim), device=dev)
+    g3 = torch.randn_like(x0)
+
+    def rollout_eval(x, zz, states):
+        with torch.no_grad():
+            for _ in range(cfg.test_steps):
+                (x, states, _sur, _pen), _dbg, _ = agent((x, zz, states), 1.0)
+        return x, states
+
+    def rollout_train(x, zz, states):
+        for _ in range(cfg.test_steps):
+            (xo, states, sur, pen), _dbg, _ = agent((x, zz, states), 0.5)
+            ((xo * g3).sum() * 1e-6 + sur.sum() + pen.sum()).backward()
+            x = xo.detach()                       # train.py:378-381: the retouched image re-enters as a leaf
+        return x, states
+
+    res3 = {"batch": B3, "steps": int(cfg.test_steps)}
+    agent.eval()
+    res3["eval_eager_ms"] = round(timed(lambda: rollout_eval(x0, z, s0), 3), 3)
+    ge = GraphedStep(rollout_eval, (x0, z, s0), modules=[agent])
+    res3["eval_graph_ms"] = round(timed(lambda: ge(x0, z, s0), 5), 3)
+    agent.train()
+    res3["train_eager_ms"] = round(timed(lambda: rollout_train(x0, z, s0), 3), 3)
+    agent.zero_grad(set_to_none=True)
+    gt = GraphedStep(rollout_train, (x0, z, s0), modules=[agent])
+    res3["train_graph_ms"] = round(timed(lambda: gt(x0, z, s0), 5), 3)
+    # ISP share: the same five heterogeneous applies alone (one selected filter per sample and step)
+    ops3 = torch.tensor([cfg.filters[int(i)].OP for i in rng.randint(0, 10, size=B3)], dtype=torch.int32, device=dev)
+    P3 = torch.full((B3, 24), 0.7, device=dev)
+    P3[:, :9] = torch.eye(3, device=dev).reshape(1, 9) * 0.8 + 0.1
+
+    def isp_only(x):
+        with torch.no_grad():
+            for _ in range(cfg.test_steps):
+                x = AF.apply_ops(x, P3, ops3, clip=True)
+        return x
+    gi = GraphedStep(isp_only, (x0,))
+    res3["isp_only_fwd_graph_ms"] = round(timed(lambda: gi(x0), 5), 3)
+    res3["nlm_samples_in_isp_only"] = int((ops3 == AF.OP_NLM).sum())
+    out["config3_rollout_b8_isp_side"] = res3
     return out
 
 
