@@ -435,6 +435,10 @@ def run_b200(args):
             "hbm_frac_step": step_bytes / 1e9 / (ms_max / args.steps / 1e3) / peak,
             "dram_floor_frac_step": bank_min_bytes / 1e9 / (ms_max / args.steps / 1e3) / peak,
             "hbm_frac_excl_nlm": pw_bytes / 1e9 / (pw_ms / 1e3) / peak,
+            # the same 9 filters inside the banked step (step time minus the NLM launches, which are the
+            # same kernels banked or not): above 1.0 because the bank reads the image once, not 9 times
+            "hbm_frac_excl_nlm_banked": (pw_bytes / 1e9 / ((ms_max / args.steps - sum(kern["NLM"])) / 1e3) / peak)
+            if "NLM" in kern else None,
             "kernels_note": "per-filter rows = the same kernels launched one filter at a time (unbanked), "
                             "measured right after the timed region",
             "kernels": klist,
