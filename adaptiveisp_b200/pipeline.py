@@ -105,7 +105,8 @@ class GraphedHostLoop:
 
     ``step_fn(*device_inputs)`` may call ``.backward()``; parameter ``.grad`` tensors become static
     (use ``zero_grad(set_to_none=False)`` between optimizer steps).  Returns nothing; the result of
-    every step is copied into ``host_out`` (a pinned tensor) asynchronously.
+    every step is copied asynchronously into ``host_out``: one pinned tensor reused for every step,
+    or a sequence of pinned tensors, one per batch.
     """
 
     class _Slot:
@@ -159,9 +160,10 @@ class GraphedHostLoop:
             s.graph.replay()
             s.done.record(cur)
             if host_out is not None:
+                dst = host_out[k] if isinstance(host_out, (list, tuple)) else host_out
                 with torch.cuda.stream(self.s_out):
                     self.s_out.wait_event(s.done)
-                    host_out.copy_(s.out, non_blocking=True)
+                    dst.copy_(s.out, non_blocking=True)
                     s.out_free.record(self.s_out)
                 self.d2h_bytes += s.out.numel() * s.out.element_size()
             n += 1
