@@ -778,11 +778,28 @@ pw_bank_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout
     pdl_prologue();
     extern __shared__ float4 sx4[];     // [GROUPS][3][kThreads] packs of VEC floats = 3 * kPwChunkPx floats
     float* sx = reinterpret_cast<float*>(sx4);
-    __shared__ float raw[1][kConst];
-    __shared__ float sc[1][kConst];
-    __shared__ int sop[1];
-    __shared__ float red[kWarps * AISP_ACC_STRIDE];
+    __shared__ float raw[kMaxBankFilters][kConst];
+    __shared__ float sc[kMaxBankFilters][kConst];
+    __shared__ int sop[kMaxBankFilters];
+    __shared__ int svs[kMaxBankFilters];
+    __shared__ float red[2][kWarps * AISP_ACC_STRIDE];   // alternating per slot: one barrier per slot suffices
     constexpr int GROUPS = kPwChunkPx / (kThreads * VEC);
+    const int n = bm.n;
+    {   // every slot's constants up front, one warp per slot (as in pw_bank_fwd_kernel)
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int j = warp; j < n; j += kWarps) {
+            const int v = bank_sample(bm, blockIdx.y * n + j);
+            raw[j][lane] = (lane < AISP_PSTRIDE) ? params[(size_t)v * AISP_PSTRIDE + lane] : 0.f;
+            sc[j][lane] = 0.f;
+            __syncwarp();
+            if (lane == 0) {
+                const int op = bank_op(bm, v);
+                sop[j] = op;
+                svs[j] = v;
+                derive_consts(op, raw[j], sc[j]);
+            }
+        }
+    }
     const float* pr = img + (size_t)blockIdx.y * 3 * (size_t)N;
     const int chunk0 = blockIdx.x * kPwChunkPx;
 #pragma unroll
@@ -801,17 +818,16 @@ pw_bank_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout
 #pragma unroll
             for (int v = 0; v < VEC; ++v) px[pl * kThreads * VEC + v] = t[pl].v[v];
     }
-    const int n = bm.n;
+    __syncthreads();
     for (int j = 0; j < n; ++j) {
-        const int b = bank_sample(bm, blockIdx.y * n + j);
-        if (j > 0) __syncthreads();   // the previous slot's constants are no longer read
-        stage_consts(params, nullptr, b, 1, 1, raw, sc, sop, bm);
+        const int b = svs[j];
         const float* pg = gout + (size_t)b * 3 * (size_t)N;
         float* dst = partial + ((size_t)b * gridDim.x + blockIdx.x) * AISP_ACC_STRIDE;
-        const float* c = sc[0];
-        switch (sop[0]) {
+        const float* c = sc[j];
+        float* redj = red[j & 1];
+        switch (sop[j]) {
 #define AISP_CASE(OPC) \
-    case OPC: pw_bank_bwd_body<OPC, VEC>(sx, pg, c, N, clip, red, dst); break;
+    case OPC: pw_bank_bwd_body<OPC, VEC>(sx, pg, c, N, clip, redj, dst); break;
             AISP_CASE(AISP_OP_EXPOSURE)
             AISP_CASE(AISP_OP_GAMMA)
             AISP_CASE(AISP_OP_WB)
