@@ -21,9 +21,20 @@ namespace aisp {
 
 constexpr int kNlmHalo = 7;                       // search radius 5 + patch radius 2
 constexpr int kNlmRows = 4;                       // output rows per thread
-constexpr int kNlmSmW = 32 + 10;                  // columns x0-7 .. x0+34
-constexpr int kNlmSmH = kNlmTileH + 2 * kNlmHalo; // rows    y0-7 .. y0+38
-static_assert(kNlmTileH == kNlmRows * kWarps, "8 warps x 4 rows");
+// Lane layout: LW lanes form one row group (LW = 32: a warp is one group of 28 output columns;
+// LW = 16: a warp is two groups of 12 output columns, stacked vertically).  The 16-lane layout serves
+// the remainder column of an image whose width leaves <= 12 columns after the 28-wide tiles (8 for
+// W = 512): those columns then cost half a tile column instead of a whole one.
+template <int LW>
+struct NlmGeo {
+    static constexpr int NG = 32 / LW;                       // row groups per warp
+    static constexpr int TW = LW - 4;                        // output columns per group
+    static constexpr int TH = kNlmRows * kWarps * NG;        // output rows per CTA
+    static constexpr int SW = LW + 10 + (LW == 16 ? 2 : 0);  // staged columns x0-7 .. x0+LW+2 (+2 pad: the two row groups
+                                                             // of a warp then sit 16 banks apart)
+    static constexpr int SH = TH + 2 * kNlmHalo;             // staged rows    y0-7 .. y0+TH+6
+};
+static_assert(NlmGeo<32>::TW == kNlmTileW && NlmGeo<32>::TH == kNlmTileH, "geometry shared with the header");
 
 __device__ __forceinline__ int wrap(int i, int n) {
     i %= n;
@@ -70,17 +81,19 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
     return r;
 }
 
-template <bool WITH_GRAD>
+template <bool WITH_GRAD, int LW>
 __global__ void __launch_bounds__(kThreads, WITH_GRAD ? 3 : 4)
 nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __restrict__ dout_dh,
            float* __restrict__ wsum_out, const float* __restrict__ params, const int32_t* __restrict__ ops, int H,
-           int W, BankMap bm) {
+           int W, int x_off, BankMap bm) {
     pdl_prologue();
+    using Geo = NlmGeo<LW>;
+    constexpr int kNlmSmH = Geo::SH, kNlmSmW = Geo::SW;
     __shared__ float sY[kNlmSmH][kNlmSmW];
     __shared__ float sC[3][kNlmSmH][kNlmSmW];
     const int b = bank_sample(bm, blockIdx.z);   // filter-bank launches: see BankMap
     if (sample_op(ops, bm, b) != AISP_OP_NLM) return;
-    const int x0 = blockIdx.x * kNlmTileW, y0 = blockIdx.y * kNlmTileH;
+    const int x0 = x_off + blockIdx.x * Geo::TW, y0 = blockIdx.y * Geo::TH;
     const size_t plane = (size_t)H * W;
     const float* src = img + (size_t)(b / bm.F) * 3 * plane;
     const size_t sb = (size_t)(b / bm.F);        // stashes stay compact: one NLM slot per image
@@ -88,13 +101,13 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
     // stage clipped RGB and luma of the wrapped tile + halo       (isp/filters.py:583, denoise.py:11-17)
     // a warp walks whole rows (row wrap once per row, column wrap by one conditional add when the
     // image is wider than the tile footprint; the generic modulo only serves tiny images)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane32 = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool wide = (W >= kNlmSmW) && (H >= kNlmSmH);
     for (int row = warp; row < kNlmSmH; row += kWarps) {
         int gy = y0 - kNlmHalo + row;
         gy = wide ? (gy < 0 ? gy + H : (gy >= H ? gy - H : gy)) : wrap(gy, H);
         const float* rp = src + (size_t)gy * W;
-        for (int col = lane; col < kNlmSmW; col += 32) {
+        for (int col = lane32; col < kNlmSmW; col += 32) {
             int gx = x0 - kNlmHalo + col;
             gx = wide ? (gx < 0 ? gx + W : (gx >= W ? gx - W : gx)) : wrap(gx, W);
             const float r = clip01(__ldg(rp + gx));
@@ -108,7 +121,8 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
     }
     __syncthreads();
 
-    const int r0 = warp * kNlmRows;  // first output row of this thread, relative to y0
+    const int lane = lane32 % LW;                               // column within the row group
+    const int r0 = (warp * Geo::NG + lane32 / LW) * kNlmRows;   // first output row of this thread, relative to y0
     const float h = params[(size_t)b * AISP_PSTRIDE];
     const float hh = fmaxf(h, 0.f) + 1e-8f;              // relu(h) + EPS   (denoise.py:112)
     const float negk = -1.4426950408889634f / hh;        // exp(-d/hh) = 2^(d * negk)
@@ -164,12 +178,12 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
             for (int i = 0; i < kNlmRows; i += 2) {
                 // 5-wide sum across lanes l .. l+4  (box centred on output column x0 + lane)
                 const f32x2 vv = pack2(v[i], v[i + 1]);
-                const f32x2 p2 = add2(vv, pack2(__shfl_down_sync(0xffffffffu, v[i], 1),
-                                                __shfl_down_sync(0xffffffffu, v[i + 1], 1)));
-                const f32x2 p4 = add2(p2, pack2(__shfl_down_sync(0xffffffffu, lo2(p2), 2),
-                                                __shfl_down_sync(0xffffffffu, hi2(p2), 2)));
-                const f32x2 box = add2(p4, pack2(__shfl_down_sync(0xffffffffu, v[i], 4),
-                                                 __shfl_down_sync(0xffffffffu, v[i + 1], 4)));
+                const f32x2 p2 = add2(vv, pack2(__shfl_down_sync(0xffffffffu, v[i], 1, LW),
+                                                __shfl_down_sync(0xffffffffu, v[i + 1], 1, LW)));
+                const f32x2 p4 = add2(p2, pack2(__shfl_down_sync(0xffffffffu, lo2(p2), 2, LW),
+                                                __shfl_down_sync(0xffffffffu, hi2(p2), 2, LW)));
+                const f32x2 box = add2(p4, pack2(__shfl_down_sync(0xffffffffu, v[i], 4, LW),
+                                                 __shfl_down_sync(0xffffffffu, v[i + 1], 4, LW)));
                 // box >= 0: the reference's relu is a no-op
                 const f32x2 dist = pack2(sqrt_approx(lo2(box)), sqrt_approx(hi2(box)));
                 const f32x2 arg = mul2(dist, negk2);
@@ -199,7 +213,7 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
     }
 
     const int gx = x0 + lane;
-    if (lane >= kNlmTileW || gx >= W) return;
+    if (lane >= Geo::TW || gx >= W) return;
     const float inv_h2 = (h > 0.f) ? 1.0f / (hh * hh) : 0.f;  // relu'(h)
     float wsum[kNlmRows], wd[kNlmRows];
 #pragma unroll
@@ -255,11 +269,28 @@ int pointwise_rows(int H, int W);
 
 cudaError_t launch_nlm_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,
                            float* dout_dh, float* wsum, BankMap bm, cudaStream_t st) {
-    dim3 grid((W + kNlmTileW - 1) / kNlmTileW, (H + kNlmTileH - 1) / kNlmTileH, B);
-    if (dout_dh)
-        launch_pdl(nlm_kernel<true>, grid, kThreads, st, img, out, dout_dh, wsum, params, ops, H, W, bm);
-    else
-        launch_pdl(nlm_kernel<false>, grid, kThreads, st, img, out, nullptr, wsum, params, ops, H, W, bm);
+    // 28-wide tiles; a remainder of <= 12 columns goes to the half-warp layout (12 columns x 64 rows per CTA)
+    using G32 = NlmGeo<32>;
+    using G16 = NlmGeo<16>;
+    int n32 = W / G32::TW;
+    const int rem = W - n32 * G32::TW;
+    const bool half = rem > 0 && rem <= G16::TW && n32 > 0;
+    if (rem > 0 && !half) ++n32;
+    if (n32 > 0) {
+        dim3 grid(n32, (H + G32::TH - 1) / G32::TH, B);
+        if (dout_dh)
+            launch_pdl(nlm_kernel<true, 32>, grid, kThreads, st, img, out, dout_dh, wsum, params, ops, H, W, 0, bm);
+        else
+            launch_pdl(nlm_kernel<false, 32>, grid, kThreads, st, img, out, nullptr, wsum, params, ops, H, W, 0, bm);
+    }
+    if (half) {
+        dim3 grid(1, (H + G16::TH - 1) / G16::TH, B);
+        const int x_off = n32 * G32::TW;
+        if (dout_dh)
+            launch_pdl(nlm_kernel<true, 16>, grid, kThreads, st, img, out, dout_dh, wsum, params, ops, H, W, x_off, bm);
+        else
+            launch_pdl(nlm_kernel<false, 16>, grid, kThreads, st, img, out, nullptr, wsum, params, ops, H, W, x_off, bm);
+    }
     return cudaGetLastError();
 }
 
