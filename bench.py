@@ -260,8 +260,9 @@ def run_b200(args):
                                    stash.data_ptr(), gP_all.data_ptr(), scratch_all.data_ptr(), scratch_all.numel(),
                                    st), "bank bwd")
 
-    # 3 family kernels forward; 3 family kernels + 3 finalize kernels backward
-    launches_per_step = 9
+    # forward: per-pixel bank, sharpen, NLM (28-wide tiles) + NLM (remainder column: 512 = 18*28 + 8);
+    # backward: 3 family kernels + 3 finalize kernels
+    launches_per_step = 10
 
     def barrier():
         if world > 1:
