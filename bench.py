@@ -370,23 +370,30 @@ def run_b200(args):
                 ft = host_feat.to(dev, non_blocking=True)
                 host_out.copy_(isp_step(x, ft).detach(), non_blocking=True)
 
+    # The PCIe links and host memory of a box are shared with whatever runs on its other GPUs, so a
+    # single 20-step window (~0.1 s) is noisy: every mode is timed over three back-to-back windows of
+    # e2e_steps steps (max over ranks each) and the MEDIAN window is reported; all three are kept.
     e2e_steps = max(3, min(args.steps, 20))
-    e2e_vals = {}
+    e2e_vals, e2e_windows = {}, {}
     win = []
     for staged in ("graph", "staged", "sync"):
         e2e_run(3, staged)
-        barrier()
-        tw2 = time.time()
-        e0.record()
-        e2e_run(e2e_steps, staged)
-        e1.record()
-        barrier()
-        tw3 = time.time()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_vals[staged] = world * px_step * e2e_steps / 1e6 / (float(t.item()) / 1e3)
-        win.append((tw2, tw3))
+        vals = []
+        for _rep in range(3):
+            barrier()
+            tw2 = time.time()
+            e0.record()
+            e2e_run(e2e_steps, staged)
+            e1.record()
+            barrier()
+            tw3 = time.time()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            vals.append(world * px_step * e2e_steps / 1e6 / (float(t.item()) / 1e3))
+            win.append((tw2, tw3))
+        e2e_windows[staged] = [round(v, 1) for v in vals]
+        e2e_vals[staged] = sorted(vals)[1]
     e2e_value = e2e_vals["graph"]
     h2d = host_img.numel() * 4 + host_feat.numel() * 4
     d2h = host_out.numel() * 4
@@ -444,7 +451,7 @@ def run_b200(args):
                             "measured right after the timed region",
             "kernels": klist,
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "pinned_numa_node": numa_node,
+                    "steps": e2e_steps, "windows": e2e_windows, "pinned_numa_node": numa_node,
                     "api": "FilterBank over the 10 drop-in Filter modules (their FC layers + regressors, one banked "
                            "kernel set) + .backward(), replayed as one CUDA graph per step by GraphedHostLoop with "
                            "double-buffered pinned-host copies",
