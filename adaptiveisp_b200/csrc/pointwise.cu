@@ -785,6 +785,11 @@ pw_bank_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout
     __shared__ float red[2][kWarps * AISP_ACC_STRIDE];   // alternating per slot: one barrier per slot suffices
     constexpr int GROUPS = kPwChunkPx / (kThreads * VEC);
     const int n = bm.n;
+    if (VEC == 4 && threadIdx.x < 3 && (blockIdx.x + 1) * kPwChunkPx <= N) {   // first slot's gradient chunk -> L2
+        const float* nx = gout + (size_t)bank_sample(bm, blockIdx.y * n) * 3 * (size_t)N + (size_t)threadIdx.x * N +
+                          (size_t)blockIdx.x * kPwChunkPx;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"((unsigned)(kPwChunkPx * sizeof(float))) : "memory");
+    }
     {   // every slot's constants up front, one warp per slot (as in pw_bank_fwd_kernel)
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         for (int j = warp; j < n; j += kWarps) {
@@ -822,6 +827,12 @@ pw_bank_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout
     for (int j = 0; j < n; ++j) {
         const int b = svs[j];
         const float* pg = gout + (size_t)b * 3 * (size_t)N;
+        // pull the next slot's upstream-gradient chunk into L2 while this slot computes (bulk prefetch:
+        // no registers, no shared memory; the demand loads of the next slot then see L2 latency)
+        if (VEC == 4 && j + 1 < n && threadIdx.x < 3 && chunk0 + kPwChunkPx <= N) {
+            const float* nx = gout + (size_t)svs[j + 1] * 3 * (size_t)N + (size_t)threadIdx.x * N + chunk0;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"((unsigned)(kPwChunkPx * sizeof(float))) : "memory");
+        }
         float* dst = partial + ((size_t)b * gridDim.x + blockIdx.x) * AISP_ACC_STRIDE;
         const float* c = sc[j];
         float* redj = red[j & 1];
