@@ -1071,6 +1071,10 @@ pw_chain_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gou
     const float* pg = gout + base;
     float* gi = GIMG ? gimg + base : nullptr;
     const int chunk0 = blockIdx.x * kPwChunkPx;
+    if (VEC == 4) {   // long compute per round (recompute + reverse sweep): later rounds then find their pixels in L2
+        prefetch_chunk_l2(pr, N, chunk0);
+        prefetch_chunk_l2(pg, N, chunk0);
+    }
     float acc[kChainMax][kChainAcc];
 #pragma unroll
     for (int k = 0; k < kChainMax; ++k)
