@@ -223,3 +223,23 @@ def test_replay_segmentation_and_reference_file_formats():
     assert [p.numel() for p in plist] == [9, 8, 1] and float(plist[1][3]) == pytest.approx(0.9)
     header, rec = replay.parse_records("E,G,CCM,Shr,NLM,T,Ct,S+,BW,W\nimg1.png,2,5,0,-1,-1\nimg2.png,4,4,4,4,4\n")
     assert header[4] == "NLM" and rec == {"img1.png": [2, 5, 0], "img2.png": [4, 4, 4, 4, 4]}
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path through the oracle port) must run without
+    a GPU and print ONE JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "isp_chain_megapixels_per_sec_fwd_bwd" and d["unit"] == "MP/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] and "sample" in d["cpu_baseline"]
+    assert d["e2e"] == {"value": d["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
