@@ -3,7 +3,6 @@ import sys
 import torch
 sys.path.insert(0, ".")
 from adaptiveisp_b200 import functional as AF, replay
-from adaptiveisp_b200.synthetic import lod_batch
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
