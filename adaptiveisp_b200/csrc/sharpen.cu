@@ -67,6 +67,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, 
         : "memory");
 }
 
+// L2 prefetch of a tile through the same tensor map (no shared memory, no barrier)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 // ---- cp.async (LDGSTS) fallback staging --------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -205,6 +212,19 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, int tma_ok, const float
         if (threadIdx.x == 0) {
             mbar_expect_tx(&bar, kTmaBytes);
             tma_load_3d(sm, &tmap, x0 - kColOff, y0 - kHalo, (b / bm.F) * 3, &bar);
+        }
+        // one wave ahead: the tile that a CTA scheduled ~one machine-fill later will load goes to L2 now
+        if (threadIdx.x == 32) {
+            const int ahead = 148 * (BWD ? 3 : 4);
+            int lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + ahead;
+            const int px = lin % gridDim.x;
+            lin /= gridDim.x;
+            const int py = lin % gridDim.y, pz = lin / gridDim.y;
+            if (pz < (int)gridDim.z) {
+                const int pb = bank_sample(bm, pz);
+                if (is_sharpen(sample_op(ops, bm, pb)))
+                    tma_prefetch_3d(&tmap, px * kShTileW - kColOff, py * kShTileH - kHalo, (pb / bm.F) * 3);
+            }
         }
     } else {
         stage_tile_cp(img + (size_t)(b / bm.F) * 3 * H * W, sm, H, W, x0, y0, vec != 0);
@@ -449,7 +469,7 @@ cudaError_t launch_sharpen_fwd(const float* img, float* out, const float* params
     CUtensorMap map;
     const int tma_ok = make_tile_map(&map, img, bm.n ? B / bm.n : B, H, W) ? 1 : 0;
     launch_pdl(sharpen_kernel<false, false>, grid, kThreads, st, map, tma_ok, img, nullptr, out, params, ops, H, W, vec,
-                                                            nullptr, bm);
+               nullptr, bm);
     return cudaGetLastError();
 }
 
@@ -462,10 +482,10 @@ cudaError_t launch_sharpen_bwd(const float* img, const float* gout, const float*
     const int tma_ok = make_tile_map(&map, img, bm.n ? B / bm.n : B, H, W) ? 1 : 0;
     if (grad_img)
         launch_pdl(sharpen_kernel<true, true>, grid, kThreads, st, map, tma_ok, img, gout, gy_scratch, params, ops, H, W, vec,
-                                                              partial, bm);
+                   partial, bm);
     else
         launch_pdl(sharpen_kernel<true, false>, grid, kThreads, st, map, tma_ok, img, gout, nullptr, params, ops, H, W, vec,
-                                                               partial, bm);
+                   partial, bm);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     e = launch_finalize(partial, sharpen_rows(H, W), params, ops, FAMILY_SHARPEN, B, grad_params, bm, st);
