@@ -7,7 +7,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 BENCH="python bench.py --steps 2 --warmup 3 --no-cpu --no-extras"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv $BENCH > $OUT/launches_$TAG.log 2>&1
-KERNELS="nlm_kernel sharpen_kernel pw_bank_fwd_kernel pw_bank_bwd_kernel"
+KERNELS=${KERNELS:-"nlm_kernel sharpen_kernel pw_bank_fwd_kernel pw_bank_bwd_kernel"}
 [ "${PERFILTER:-0}" = 1 ] && KERNELS="nlm_kernel sharpen_kernel pw_fwd_kernel pw_bwd_kernel"
 for K in $KERNELS; do
   # the first launches of every kernel are the banked ones (all slots of a family in one launch);
