@@ -58,3 +58,19 @@ def test_flat_grad_allreduce_world2_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_numa_helpers_are_safe_without_a_gpu():
+    """The pinned-buffer NUMA placement is best effort: without sysfs information (no GPU, VM) it
+    reports node -1 and leaves the affinity mask alone."""
+    import os
+    from adaptiveisp_b200 import dist as D
+    assert D._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert D._parse_cpulist("") == []
+    before = os.sched_getaffinity(0)
+    node, prev = D.bind_to_gpu_numa_node(0)
+    assert prev == before
+    if node < 0:
+        assert os.sched_getaffinity(0) == before
+    else:
+        os.sched_setaffinity(0, prev)
