@@ -422,7 +422,8 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "height": H, "width": W, "filters": names,
-                       "l2": "inputs (201 MB image + 201 MB upstream gradient per GPU) exceed the 126 MB L2; no flush",
+                       "l2": "per step and GPU: 201 MB image, 2.0 GB of upstream gradients (one per filter) read, 2.0 GB "
+                             "output stack written -- far beyond the 126 MB L2; no flush",
                        "parallelism": f"dp{world} (batch-sharded replicas, no collective in the ISP path)"},
             "roofline": {"bound": "hbm", "kernel": ("nlm_kernel<grad>" if dom["filter"] == "NLM" else dom["filter"]) +
                          (" fwd" if dom_fwd else " bwd"), "achieved": ach, "peak": peak, "unit": "GB/s",
