@@ -18,9 +18,10 @@ LIB_PATH = os.path.join(CSRC, "libaisp_b200.so")
 
 PSTRIDE = 24
 MAX_STEPS = 8
-MAX_CHAIN_BWD = 4
+MAX_CHAIN_BWD = 6
 MAX_BANK_FILTERS = 16
-ABI_VERSION = 2
+SEQ_CLIP, SEQ_STRICT = 1, 2   # bits of `clip_each` in the sequence entry points
+ABI_VERSION = 3
 
 # name -> (restype, argtypes); mirrors include/aisp_b200.h one to one
 _P = c_void_p
@@ -113,15 +114,12 @@ def stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-_scratch: dict = {}
-
-
 def scratch(B: int, H: int, W: int, device: torch.device) -> torch.Tensor:
-    """Per-(device, stream) grow-only partial-sum buffer for the backward kernels."""
+    """Partial-sum buffer for one backward call (``aisp_bwd_scratch_bytes``).
+
+    Allocated per call from the caching allocator: that costs no cudaMalloc in steady state and is
+    safe under CUDA-graph capture (the block comes from the graph's private pool and lives as long
+    as the graph does) -- a cached grow-only buffer would be dropped on growth while a captured
+    graph still writes to it on replay."""
     need = lib().aisp_bwd_scratch_bytes(B, H, W)
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    buf = _scratch.get(key)
-    if buf is None or buf.numel() < need:
-        buf = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
-        _scratch[key] = buf
-    return buf
+    return torch.empty(max(need, 1 << 12), dtype=torch.uint8, device=device)

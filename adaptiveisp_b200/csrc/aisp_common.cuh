@@ -117,6 +117,17 @@ __device__ __forceinline__ float clip01(float y) {
     asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(r));
     return r;
 }
+// torch.maximum / torch.minimum / Tensor.max(dim) semantics: NaN wins (fmaxf / fminf drop it)
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float min_nan(float a, float b) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
 // clamp backward: gradient passes iff lo <= y <= hi, inclusive (NaN -> 0)
 __device__ __forceinline__ float pass01(float y) { return (y >= 0.f && y <= 1.f) ? 1.f : 0.f; }
 

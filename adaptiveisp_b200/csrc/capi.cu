@@ -45,7 +45,7 @@ inline int shape_ok(int B, int H, int W) {
 
 extern "C" {
 
-int aisp_version(void) { return 2; }
+int aisp_version(void) { return 3; }
 
 const char* aisp_status_string(int s) {
     switch (s) {
@@ -77,7 +77,7 @@ int aisp_pointwise_fwd(const float* img, float* out, const float* params, const 
     if (!shape_ok(B, H, W) || S < 1 || S > AISP_MAX_STEPS) return AISP_ERR_SHAPE;
     if (!al4(img) || !al4(out)) return AISP_ERR_ALIGN;
     if (img == out) return AISP_ERR_UNSUPPORTED;
-    return (int)launch_pointwise_fwd(img, out, params, ops, seq_len, B, H, W, S, clip_each ? 1 : 0, plain_batch(),
+    return (int)launch_pointwise_fwd(img, out, params, ops, seq_len, B, H, W, S, clip_each & 3, plain_batch(),
                                      (cudaStream_t)stream);
 }
 
@@ -100,7 +100,7 @@ int aisp_pointwise_chain_bwd(const float* img, const float* grad_out, const floa
     if (S > AISP_MAX_CHAIN_BWD || S > chain_bwd_max_steps()) return AISP_ERR_UNSUPPORTED;
     if (scratch_bytes < aisp_bwd_scratch_bytes(B, H, W)) return AISP_ERR_SCRATCH;
     if (!al4(img) || !al4(grad_out) || !al4(grad_img)) return AISP_ERR_ALIGN;
-    return (int)launch_pointwise_chain_bwd(img, grad_out, params, ops, seq_len, B, H, W, S, clip_each ? 1 : 0,
+    return (int)launch_pointwise_chain_bwd(img, grad_out, params, ops, seq_len, B, H, W, S, clip_each & 3,
                                            grad_params, grad_img, (float*)scratch, (cudaStream_t)stream);
 }
 

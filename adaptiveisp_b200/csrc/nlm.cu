@@ -229,7 +229,9 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
         if (wsum_out) wsum_out[sb * plane + (size_t)gy * W + gx] = wsum[i];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float y = ac[c][i] * iw;
+            // 0 * x with the UNclipped centre pixel: the (1 - mask) * img term of the reference's lerp
+            // (isp/filters.py:115), NaN iff the input pixel is inf / NaN (an L2 hit: the tile was just staged)
+            const float y = fmaf(0.f, __ldg(src + (size_t)c * plane + (size_t)gy * W + gx), ac[c][i] * iw);
             const size_t o = (size_t)b * 3 * plane + (size_t)c * plane + (size_t)gy * W + gx;
             out[o] = clip01(y);
             if (WITH_GRAD)

@@ -204,8 +204,11 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, int tma_ok, const float
     const int x0 = blockIdx.x * kShTileW, y0 = blockIdx.y * kShTileH;
     const size_t base = (size_t)b * 3 * H * W;
     const bool frame_tile = (x0 == 0) || (y0 == 0) || (x0 + kShTileW >= W) || (y0 + kShTileH >= H);  // CTA-uniform
-    // zero-filled out-of-bounds halos are only wrong for reflect padding at the frame
-    const bool use_tma = tma_ok && !(op == AISP_OP_USM && frame_tile);
+    // zero-filled out-of-bounds halos are only wrong for reflect padding: a USM tile takes the
+    // reflecting cp.async path as soon as its 2-px HALO leaves the image (H = y0 + 17 puts halo row
+    // y0 + 17 == H outside although the tile itself ends one row short of the frame)
+    const bool usm_halo_out = (x0 < kHalo) || (y0 < kHalo) || (x0 + kShTileW + kHalo > W) || (y0 + kShTileH + kHalo > H);
+    const bool use_tma = tma_ok && !(op == AISP_OP_USM && usm_halo_out);
     if (use_tma) {
         if (threadIdx.x == 0) mbar_init(&bar, 1);
         __syncthreads();
@@ -280,7 +283,8 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, int tma_ok, const float
             const size_t off = base + ((size_t)ch * H + gy) * W + gx0;
             float y[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) y[i] = sharpen_value(op, xc[r][i], blur[r][i], f);
+            for (int i = 0; i < 4; ++i)   // 0 * x: the (1 - mask) * img term of the reference's lerp (NaN iff x is inf / NaN)
+                y[i] = fmaf(0.f, xc[r][i], sharpen_value(op, xc[r][i], blur[r][i], f));
             if (!BWD) {
                 if (vec_ok) {
                     stg_stream4(out + off, make_float4(clip01(y[0]), clip01(y[1]), clip01(y[2]), clip01(y[3])));

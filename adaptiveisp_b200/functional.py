@@ -293,7 +293,7 @@ class _ApplyChain(torch.autograd.Function):
         out = torch.empty_like(img)
         with torch.cuda.device(img.device):
             rc = _lib.lib().aisp_pointwise_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), ops.data_ptr(),
-                                               _lib.ptr(seq_len), B, H, W, S, int(clip_each),
+                                               _lib.ptr(seq_len), B, H, W, S, int(clip_each) | _lib.SEQ_STRICT,
                                                _lib.stream_ptr(img.device))
         _lib.check(rc, "aisp_pointwise_fwd")
         ctx.save_for_backward(img, P, ops, seq_len)
@@ -314,7 +314,8 @@ class _ApplyChain(torch.autograd.Function):
         sc = _lib.scratch(B, H, W, img.device)
         with torch.cuda.device(img.device):
             rc = _lib.lib().aisp_pointwise_chain_bwd(img.data_ptr(), g.data_ptr(), P.data_ptr(), ops.data_ptr(),
-                                                     _lib.ptr(seq_len), B, H, W, S, int(ctx.clip_each), gP.data_ptr(),
+                                                     _lib.ptr(seq_len), B, H, W, S,
+                                                     int(ctx.clip_each) | _lib.SEQ_STRICT, gP.data_ptr(),
                                                      _lib.ptr(gimg), sc.data_ptr(), sc.numel(),
                                                      _lib.stream_ptr(img.device))
         _lib.check(rc, "aisp_pointwise_chain_bwd")
@@ -327,7 +328,10 @@ def apply_chain(img: torch.Tensor, P: torch.Tensor, ops: torch.Tensor, seq_len: 
     with parameter rows ``P[b, k]``; forward in one pass over HBM, backward in one pass.
 
     img ``[B,3,H,W]``; P ``[B,S,PSTRIDE]`` (may require grad); ops int32 ``[B,S]`` with ``S <= MAX_CHAIN_BWD``
-    when gradients are needed.  ``clip_each`` as in :func:`chain_forward`.
+    (6) when gradients are needed.  ``clip_each`` as in :func:`chain_forward`.  Every per-pixel op is
+    differentiated, ColorFilter included.  The ops live on the device and are not read back: a sample
+    whose sequence holds a stencil op (Shr / USM / NLM -- use :func:`run_pipeline` or the replay plan
+    for those) or an unknown code gets an all-NaN output and NaN gradients, never stale memory.
     """
     B = img.shape[0]
     S = ops.shape[1]
@@ -367,11 +371,14 @@ def image_stats(down: torch.Tensor):
 
 @torch.no_grad()
 def chain_forward(img: torch.Tensor, P: torch.Tensor, ops: torch.Tensor, seq_len: Optional[torch.Tensor] = None,
-                  clip_each: bool = True) -> torch.Tensor:
+                  clip_each: bool = True, strict: bool = True) -> torch.Tensor:
     """Per-sample sequences of per-pixel filters fused into ONE pass over HBM (forward only).
 
     img ``[B,3,H,W]``; P ``[B,S,PSTRIDE]``; ops int32 ``[B,S]``; seq_len int32 ``[B]`` or None.
-    Stencil ops are not allowed inside a fused sequence (use ``run_pipeline`` for mixed sequences).
+    Stencil ops are not allowed inside a fused sequence (use ``run_pipeline`` for mixed sequences):
+    with ``strict`` (default) such a sample's output is all NaN; ``strict=False`` gives the C ABI's
+    select-apply behaviour (samples led by a stencil op are left untouched for the stencil launches of
+    the same phase -- what :mod:`replay` relies on -- and a later stencil op ends the sequence).
     """
     _lib.require_image(img, "img")
     B, _, H, W = img.shape
@@ -386,7 +393,9 @@ def chain_forward(img: torch.Tensor, P: torch.Tensor, ops: torch.Tensor, seq_len
     out = torch.empty_like(img)
     with torch.cuda.device(img.device):
         rc = _lib.lib().aisp_pointwise_fwd(img.data_ptr(), out.data_ptr(), P.contiguous().data_ptr(), ops.data_ptr(),
-                                           _lib.ptr(seq_len), B, H, W, S, int(clip_each), _lib.stream_ptr(img.device))
+                                           _lib.ptr(seq_len), B, H, W, S,
+                                           int(clip_each) | (_lib.SEQ_STRICT if strict else 0),
+                                           _lib.stream_ptr(img.device))
     _lib.check(rc, "aisp_pointwise_fwd")
     return out
 

@@ -23,6 +23,28 @@ from typing import Iterable, Iterator, Sequence, Tuple
 import torch
 
 
+def _static_grads(modules, step_fn, example_inputs, dev, warmup):
+    """Warm `step_fn` up on a side stream, then give every parameter that received a gradient a
+    STATIC zero ``.grad`` tensor (parameters that never get one -- ``fc_mask.*`` -- keep ``None``, as in the
+    reference).  Captured with these in place, every graph ACCUMULATES into the same tensors on
+    replay, whichever slot it belongs to; callers clear them with ``zero_grad(set_to_none=False)``."""
+    for m in modules:
+        m.zero_grad(set_to_none=True)
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(max(1, warmup)):
+            step_fn(*example_inputs)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    static = []
+    for m in modules:
+        for p in m.parameters():
+            if p.grad is not None:
+                p.grad = torch.zeros_like(p)
+                static.append(p.grad)
+    return static
+
+
 class HostStagedLoop:
     def __init__(self, device, depth: int = 2):
         self.dev = torch.device(device)
@@ -103,8 +125,9 @@ class GraphedHostLoop:
         loop = GraphedHostLoop(step_fn, example_inputs=(x_dev, feat_dev), modules=filters)
         loop.run(host_batches, host_out)        # host_batches: iterable of tuples of pinned tensors
 
-    ``step_fn(*device_inputs)`` may call ``.backward()``; parameter ``.grad`` tensors become static
-    (use ``zero_grad(set_to_none=False)`` between optimizer steps).  Returns nothing; the result of
+    ``step_fn(*device_inputs)`` may call ``.backward()``; parameter ``.grad`` tensors become static and
+    every replay (of any slot) ACCUMULATES into them, like an eager ``backward()`` without
+    ``zero_grad`` (use ``zero_grad(set_to_none=False)`` between optimizer steps).  Returns nothing; the result of
     every step is copied asynchronously into ``host_out``: one pinned tensor reused for every step,
     or a sequence of pinned tensors, one per batch.
     """
@@ -119,20 +142,13 @@ class GraphedHostLoop:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.slots = []
-        side = torch.cuda.Stream(self.dev)
-        for m in modules:
-            m.zero_grad(set_to_none=True)
-        side.wait_stream(torch.cuda.current_stream(self.dev))
-        with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):
-                step_fn(*example_inputs)
-        torch.cuda.current_stream(self.dev).wait_stream(side)
-        for m in modules:
-            m.zero_grad(set_to_none=True)
+        self.static_grads = _static_grads(modules, step_fn, example_inputs, self.dev, warmup)
         for _ in range(max(1, slots)):
             s = GraphedHostLoop._Slot()
             s.inputs = tuple(t.clone() for t in example_inputs)
             s.graph = torch.cuda.CUDAGraph()
+            for g in self.static_grads:      # same .grad state (allocated, zero) before EVERY capture
+                g.zero_()
             with torch.cuda.graph(s.graph):
                 s.out = step_fn(*s.inputs)
             s.ready = torch.cuda.Event()
@@ -178,7 +194,7 @@ class GraphedStep:
     On a B200 the eager Agent step is CPU-launch-bound (about 7 ms of launches for 1.5-3.5 ms of GPU
     work, ``scripts/agent_step_timing.py``); replaying it as a graph removes that.  Shapes and the
     set of modules must stay fixed; ``step_fn`` may call ``.backward()`` (parameter ``.grad`` tensors
-    become static: clear them with ``zero_grad(set_to_none=False)``).
+    become static and each replay accumulates into them: clear them with ``zero_grad(set_to_none=False)``).
 
         g = GraphedStep(step_fn, example_inputs=(x, z, states), modules=[agent])
         out = g(x_new, z_new, states_new)       # copies into the static inputs, replays, returns static outputs
@@ -186,16 +202,7 @@ class GraphedStep:
 
     def __init__(self, step_fn, example_inputs, modules=(), warmup: int = 2):
         dev = example_inputs[0].device
-        for m in modules:
-            m.zero_grad(set_to_none=True)
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):
-                step_fn(*example_inputs)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        for m in modules:
-            m.zero_grad(set_to_none=True)
+        self.static_grads = _static_grads(modules, step_fn, example_inputs, dev, warmup)
         self.inputs = tuple(t.clone() for t in example_inputs)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):

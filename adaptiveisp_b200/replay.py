@@ -110,7 +110,7 @@ def execute_plan(img: torch.Tensor, plan: PipelinePlan, clip_each: bool = True) 
     B, _, H, W = img.shape
     x = img
     for ph in plan.phases:
-        nxt = AF.chain_forward(x, ph.params, ph.ops, ph.seq_len, clip_each)
+        nxt = AF.chain_forward(x, ph.params, ph.ops, ph.seq_len, clip_each, strict=False)
         st = _lib.stream_ptr(img.device)
         with torch.cuda.device(img.device):
             if ph.has_sharpen:

@@ -90,6 +90,14 @@ class DeviceReplayPool:
         chosen: List[int] = []
         while len(chosen) < batch_size:
             if not self._live:
+                # every record that is not in `chosen` is checked out by a caller who has not called
+                # put_back / discard yet: nothing to draw from and nothing to refill
+                if not self._free:
+                    for s in chosen:
+                        self._live.append(s)
+                    raise RuntimeError(
+                        f"replay pool exhausted: {self.capacity - len(chosen)} of {self.capacity} records are "
+                        f"checked out (get_batch without put_back/discard); cannot draw {batch_size}")
                 self.fill()
             self.rng.shuffle(self._live)
             while self._live and len(chosen) < batch_size:

@@ -53,7 +53,12 @@ enum aisp_op {
 #define AISP_PSTRIDE   24 /* floats per (sample, step) parameter row */
 #define AISP_MAX_STEPS 8  /* longest fused per-sample sequence        */
 #define AISP_ACC_STRIDE 32 /* floats per partial-sum row in the backward scratch */
-#define AISP_MAX_CHAIN_BWD 4 /* longest per-sample sequence differentiated in one fused pass */
+#define AISP_MAX_CHAIN_BWD 6 /* longest per-sample sequence differentiated in one fused pass */
+
+/* `clip_each` of the sequence entry points is a bit field: */
+#define AISP_SEQ_CLIP   1 /* clip to [0,1] after every step (Filter.forward); 0: Filter.run semantics */
+#define AISP_SEQ_STRICT 2 /* a non-per-pixel op anywhere in a sample's sequence poisons that sample's
+                             output / gradients with NaN instead of being skipped or ending the sequence */
 
 enum aisp_status {
     AISP_OK              = 0,
@@ -84,6 +89,8 @@ int aisp_op_num_params(int op);
  * Samples whose FIRST op is a stencil op (SHARPEN, SHARPEN_V2, USM, NLM) are skipped entirely
  * (their `out` rows are left untouched) so that the three family entry points can be issued
  * back to back on a heterogeneous batch; a stencil op later in a sequence ends the sequence there.
+ * With AISP_SEQ_STRICT set in `clip_each` such samples get an all-NaN `out` instead: callers that
+ * own the whole sequence (fused chains, replay) then never read uninitialised memory.
  */
 int aisp_pointwise_fwd(const float* img, float* out, const float* params, const int32_t* ops,
                        const int32_t* seq_len, int B, int H, int W, int S, int clip_each, void* stream);
@@ -110,12 +117,14 @@ int aisp_pointwise_bwd(const float* img, const float* grad_out, const float* par
 /*
  * Backward of a fused per-sample SEQUENCE of per-pixel filters (the forward is aisp_pointwise_fwd with
  * the same params / ops / seq_len / clip_each) in ONE pass over HBM: the chain is recomputed per
- * pixel in registers and swept in reverse, so the traffic is that of a single-step backward however
- * many stages are fused.  S <= AISP_MAX_CHAIN_BWD (longer chains: split them and pass grad_img on).
- *   grad_params [B,S,AISP_PSTRIDE]   rows of steps >= seq_len[b] are zero
- *   grad_img    [B,3,H,W] or NULL
- * COLOR inside a fused backward sequence yields a NaN gradient row (27 partial sums do not fit the
- * per-stage register budget); use the single-step aisp_pointwise_bwd for it.
+ * pixel (stage inputs parked in shared memory) and swept in reverse, so the traffic is that of a
+ * single-step backward however many stages are fused.  S <= AISP_MAX_CHAIN_BWD (longer chains: split
+ * them and pass grad_img on).  Every per-pixel op is differentiated, the 24-knot COLOR included
+ * (sequences containing it take a slower one-CTA-per-sample path).
+ *   grad_params [B,S,AISP_PSTRIDE]   rows of steps >= seq_len[b] (and of skipped samples) are zero
+ *   grad_img    [B,3,H,W] or NULL    rows of skipped samples are left untouched
+ *   scratch     >= aisp_bwd_scratch_bytes(B,H,W)
+ * AISP_SEQ_STRICT: samples with a non-per-pixel op get NaN grad_params rows and a NaN grad_img.
  */
 int aisp_pointwise_chain_bwd(const float* img, const float* grad_out, const float* params, const int32_t* ops,
                              const int32_t* seq_len, int B, int H, int W, int S, int clip_each,

@@ -1,0 +1,448 @@
+"""GPU parity tests added in round 2: BASELINE's own configurations at their own sizes, per-element
+gradient error, NaN / inf propagation, the drop-in surface that had no GPU coverage, the USM frame
+rule, and the fused sequence backward (up to 6 stages, ColorFilter included).
+
+Tolerances (north star): outputs max-abs <= 1e-5 on [0,1] images; parameter gradients <= 1e-4
+RELATIVE PER ELEMENT, where an element smaller than GRAD_FLOOR (1 %) of its tensor's largest entry
+is measured against that floor (below it the reference's own fp32 summation noise dominates).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import isp_oracle as O
+from tests import cases
+from tests.test_gpu_parity import OUT_ATOL, GRAD_RTOL, cls_for, out_err, rel_err, _bank_params  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+GRAD_FLOOR = 1e-2
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def F(dev):
+    from adaptiveisp_b200 import _lib, filters
+    _lib.lib()
+    return filters
+
+
+@pytest.fixture(scope="module")
+def cfg():
+    from adaptiveisp_b200.config import make_cfg
+    return make_cfg()
+
+
+def elem_err(a, b, floor=GRAD_FLOOR):
+    """Worst per-element relative error |a-b| / max(|b|, floor * max|b|) and where it occurs."""
+    a = np.asarray(a, np.float64).reshape(-1)
+    b = np.asarray(b, np.float64).reshape(-1)
+    den = np.maximum(np.abs(b), floor * max(np.abs(b).max(), 1e-30))
+    e = np.abs(a - b) / den
+    i = int(np.argmax(e))
+    return float(e[i]), i
+
+
+def assert_grad(a, b, tol, tag):
+    e, i = elem_err(a, b)
+    assert e <= tol, f"{tag}: worst component {i}: got {np.asarray(a).reshape(-1)[i]:.8g} " \
+                     f"want {np.asarray(b).reshape(-1)[i]:.8g} (per-element rel err {e:.3g} > {tol})"
+
+
+class Checks:
+    """Collects every violated bound of a test and reports them together (one GPU run shows them all)."""
+
+    def __init__(self):
+        self.bad = []
+
+    def out(self, got, ref, tol, tag):
+        e = out_err(got, ref)
+        if not e <= tol:
+            self.bad.append(f"{tag}: output err {e:.3g} > {tol}")
+
+    def grad(self, a, b, tol, tag):
+        e, i = elem_err(a, b)
+        if not e <= tol:
+            self.bad.append(f"{tag}: component {i} got {np.asarray(a).reshape(-1)[i]:.8g} want "
+                            f"{np.asarray(b).reshape(-1)[i]:.8g} (per-element rel err {e:.3g} > {tol})")
+
+    def norm(self, a, b, tol, tag):
+        e = rel_err(a, b)
+        if not e <= tol:
+            self.bad.append(f"{tag}: norm-wise rel err {e:.3g} > {tol}")
+
+    def done(self):
+        assert not self.bad, "\n".join(self.bad)
+
+
+# ----------------------------------------------------------------------------------------------
+# 1. BASELINE configs[1] at its own size: 64 x 3 x 512 x 512, ten filters, forward + backward
+# ----------------------------------------------------------------------------------------------
+def test_config2_full_size_bank_vs_oracle(dev):
+    """The bench workload itself: FilterBank stack and all ten parameter-gradient rows at B=64, 512x512
+    (262k-pixel reductions: 64 scratch rows per sample -> fp64 finalize), compared with the CPU oracle
+    on two images of the batch (NLM on one: ~8k ATen ops at 512x512 per call)."""
+    from adaptiveisp_b200 import functional as AF
+    ops = cases.AGENT_OPS
+    B, H, W = 64, 512, 512
+    Fn = len(ops)
+    img = cases.lod_batch(B, H, W, seed=1235)
+    P, plist = _bank_params(ops, B, seed=500)
+    gen = torch.Generator(device=dev).manual_seed(77)
+    g = torch.randn((B, Fn, 3, H, W), device=dev, generator=gen)
+    g[:, ops.index(O.OP_NLM)].abs_()       # d/dh under a random-sign g: the reference's own fp32 sum is noise
+    Pd = P.to(dev).requires_grad_(True)
+    y = AF.apply_bank(img.to(dev), Pd, ops, clip=True)
+    (y * g).sum().backward()
+    torch.cuda.synchronize()
+    checked, chk = 0, Checks()
+    for b in (5, 40):
+        for f, op in enumerate(ops):
+            if op == O.OP_NLM and b != 5:
+                continue
+            pc = plist[f][b:b + 1].clone().requires_grad_(True)
+            yc = O.forward(op, img[b:b + 1], pc)
+            (yc * g[b:b + 1, f].cpu()).sum().backward()
+            tag = f"image {b} {O.OP_NAMES[op]}"
+            chk.out(y[b:b + 1, f].detach().cpu().numpy(), yc.detach().numpy(), OUT_ATOL, tag)
+            n = O.OP_NPARAMS[op]
+            chk.grad(Pd.grad[b, f, :n].cpu().numpy(), pc.grad.reshape(-1).numpy(), GRAD_RTOL, tag)
+            checked += 1
+    chk.done()
+    assert checked == 19
+
+
+def test_config2_full_size_agent_select_vs_oracle(dev):
+    """Agent semantics at the bench size: ONE selected filter per sample (heterogeneous launch, B=64,
+    512x512), outputs and parameter gradients of a sample per filter against the oracle."""
+    from adaptiveisp_b200 import functional as AF
+    B, H, W = 64, 512, 512
+    rng = np.random.RandomState(3)
+    ops = [cases.AGENT_OPS[i % 10] for i in range(B)]
+    rng.shuffle(ops)
+    img = cases.lod_batch(B, H, W, seed=1240)
+    rows, plist = [], []
+    for b, op in enumerate(ops):
+        _, p = cases.params_for(op, 1, seed=900 + b)
+        plist.append(p)
+        rows.append(AF.pack_params(p, O.OP_NPARAMS[op]))
+    Pd = torch.cat(rows, 0).to(dev).requires_grad_(True)
+    gen = torch.Generator(device=dev).manual_seed(78)
+    g = torch.randn((B, 3, H, W), device=dev, generator=gen)
+    for b, op in enumerate(ops):
+        if op == O.OP_NLM:
+            g[b].abs_()
+    y = AF.apply_ops(img.to(dev), Pd, torch.tensor(ops, dtype=torch.int32, device=dev), clip=True)
+    (y * g).sum().backward()
+    torch.cuda.synchronize()
+    seen, chk = set(), Checks()
+    for b, op in enumerate(ops):
+        if op in seen:
+            continue
+        seen.add(op)
+        pc = plist[b].clone().requires_grad_(True)
+        yc = O.forward(op, img[b:b + 1], pc)
+        (yc * g[b:b + 1].cpu()).sum().backward()
+        tag = f"sample {b} {O.OP_NAMES[op]}"
+        chk.out(y[b:b + 1].detach().cpu().numpy(), yc.detach().numpy(), OUT_ATOL, tag)
+        n = O.OP_NPARAMS[op]
+        chk.grad(Pd.grad[b, :n].cpu().numpy(), pc.grad.reshape(-1).numpy(), GRAD_RTOL, tag)
+    chk.done()
+    assert len(seen) == 10
+
+
+# ----------------------------------------------------------------------------------------------
+# 2. BASELINE configs[3] (4K, desaturation / NLM / USM) backward
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("op", [O.OP_WNB, O.OP_NLM, O.OP_USM])
+def test_config4_4k_backward_on_windows(dev, op):
+    """d/dp (BW), d/dh (NLM), d/dsigma and d/damount (USM) at 3840x2160.  A parameter gradient is a sum
+    over the whole frame, which the CPU oracle cannot differentiate at 4K (7.6k image-sized autograd
+    temporaries for NLM); so the upstream gradient is supported on a window, the oracle runs on the
+    crop around it (window + the stencil's dependency radius) and must give the same number."""
+    from adaptiveisp_b200 import functional as AF
+    B, H, W = 2, 2160, 3840
+    img = cases.lod_batch(B, H, W, seed=1237, letterbox=False)
+    m, cs = 12, 96                                   # margin >= 7 (NLM) / 2 (USM); crop size
+    wins = [(700, 1500), (2160 - cs, 3840 - cs)]     # an interior window and the bottom-right corner
+    pv = {O.OP_WNB: [[0.35], [0.55]], O.OP_NLM: [[0.25], [0.55]], O.OP_USM: [[0.9, 1.2], [1.4, 0.7]]}[op]
+    p = torch.tensor(pv)
+    g = torch.zeros((B, 3, H, W))
+    gw = cases.grad_out((B, 3, cs - 2 * m, cs - 2 * m), 41)
+    if op == O.OP_NLM:
+        gw = gw.abs()
+    for b, (y0, x0) in enumerate(wins):
+        g[b, :, y0 + m:y0 + cs - m, x0 + m:x0 + cs - m] = gw[b]
+    Pd = AF.pack_params(p, O.OP_NPARAMS[op]).to(dev).requires_grad_(True)
+    xd = img.to(dev).requires_grad_(op != O.OP_NLM)          # the NLM image gradient is the slow rare path
+    y = AF.apply_ops(xd, Pd, op, clip=True)
+    (y * g.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    for b, (y0, x0) in enumerate(wins):
+        # the corner window sits on the frame: take the crop so that the frame rule is the image's own
+        # (USM reflects, the 3x3 keeps the border); NLM wraps circularly, which no crop reproduces, so its
+        # corner window is moved one radius inside
+        if op == O.OP_NLM and b == 1:
+            continue
+        xc = img[b:b + 1, :, y0:y0 + cs, x0:x0 + cs].clone().requires_grad_(True)
+        pc = p[b:b + 1].clone().requires_grad_(True)
+        yc = O.forward(op, xc, pc)
+        gc = g[b:b + 1, :, y0:y0 + cs, x0:x0 + cs]
+        (yc * gc).sum().backward()
+        tag = f"{O.OP_NAMES[op]} window {b}"
+        got = y[b:b + 1, :, y0 + m:y0 + cs - m, x0 + m:x0 + cs - m].detach().cpu().numpy()
+        assert out_err(got, yc[:, :, m:cs - m, m:cs - m].detach().numpy()) <= OUT_ATOL, tag
+        n = O.OP_NPARAMS[op]
+        assert_grad(Pd.grad[b, :n].cpu().numpy(), pc.grad.reshape(-1).numpy(), 2 * GRAD_RTOL, tag)
+        if op != O.OP_NLM:
+            gi = xd.grad[b:b + 1, :, y0 + m:y0 + cs - m, x0 + m:x0 + cs - m].cpu().numpy()
+            assert rel_err(gi, xc.grad[:, :, m:cs - m, m:cs - m].numpy()) <= GRAD_RTOL, tag
+
+
+# ----------------------------------------------------------------------------------------------
+# 3. drop-in surface without GPU coverage so far: ToneFilterV2.process, run_v2, predict_param
+# ----------------------------------------------------------------------------------------------
+def test_tone_v2_flat_params_run_v2_predict_param(F, cfg, dev):
+    """isp/filters.py:365-387 (flat [B,8] curve), :141-152 (run_v2: parameter without the batch dim),
+    :154-159 (predict_param: features -> regressor -> unclipped process)."""
+    B, H, W = 3, 40, 52
+    img = cases.edge_image(B, H, W, seed=5)
+    _, p5 = cases.params_for(O.OP_TONE, B, seed=5)            # [B,8,1,1,1]
+    flat = p5.reshape(B, 8)
+    ref = O.run(O.OP_TONE, img, p5)
+    v2 = F.ToneFilterV2(cfg, predict=True).to(dev)
+    pd = flat.to(dev).requires_grad_(True)
+    got = v2.process(img.to(dev), pd)                         # flat layout, as the reference's V2 expects
+    assert out_err(got.detach().cpu().numpy(), ref.numpy()) <= OUT_ATOL
+    g = cases.grad_out(img.shape, 5)
+    (got * g.to(dev)).sum().backward()
+    pc = p5.clone().requires_grad_(True)
+    (O.run(O.OP_TONE, img, pc) * g).sum().backward()
+    assert_grad(pd.grad.cpu().numpy(), pc.grad.reshape(B, 8).numpy(), GRAD_RTOL, "ToneFilterV2.process d/dp")
+    # run_v2: one parameter row for a single image
+    one = v2.run_v2(img[:1].to(dev), flat[0].to(dev))
+    assert out_err(one.cpu().numpy(), ref[:1].numpy()) <= OUT_ATOL
+    e = F.ExposureFilter(cfg).to(dev)
+    assert out_err(e.run_v2(img[:1].to(dev), torch.tensor([0.7], device=dev)).cpu().numpy(),
+                   O.run(O.OP_EXPOSURE, img[:1], torch.tensor([[0.7]])).numpy()) <= OUT_ATOL
+    # predict_param: features through the module's own FC layers, no clip
+    torch.manual_seed(4)
+    for cls in (F.GammaFilter, F.CCMFilter, F.SharpenFilter, F.ToneFilter):
+        flt = cls(cfg, predict=True).to(dev)
+        feats = torch.randn((B, cfg.feature_extractor_dims), device=dev) * 0.05
+        out = flt.predict_param(img.to(dev), feats)
+        with torch.no_grad():
+            raw, _ = flt.extract_parameters(feats)
+            p = flt.filter_param_regressor(raw).cpu()
+        assert out_err(out.detach().cpu().numpy(), O.run(flt.OP, img, p).numpy()) <= OUT_ATOL, cls.__name__
+        assert flt.mask.shape == (1, 1, 1, 1)
+
+
+# ----------------------------------------------------------------------------------------------
+# 4. non-finite pixels propagate as in ATen (so that the guard of train.py:374 fires on the same batches)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("op", cases.POINTWISE_OPS + [O.OP_SHARPEN, O.OP_USM])
+@pytest.mark.parametrize("clip", [True, False])
+def test_nonfinite_inputs_propagate_like_the_reference(F, cfg, dev, op, clip):
+    """NaN and +-inf planted in single channels: the set of non-finite output values must be the
+    reference's, element for element (torch.clamp / maximum / max(dim) keep NaN, and the wrapper's
+    lerp `0 * img + process` turns an inf pixel into NaN), and every finite value must still match."""
+    B, H, W = 2, 12, 16
+    img = cases.edge_image(B, H, W, seed=13, in_range=True)
+    nan, inf = float("nan"), float("inf")
+    img[0, 0, 3, 3] = nan
+    img[0, 1, 3, 6] = nan
+    img[0, 2, 5, 9] = nan
+    img[1, 0, 4, 4] = inf
+    img[1, 1, 6, 7] = -inf
+    img[1, 2, 8, 2] = inf
+    img[1, :, 9, 9] = nan
+    _, p = cases.params_for(op, B, seed=13)
+    ref = (O.forward if clip else O.run)(op, img, p)
+    flt = cls_for(F, op)(cfg).to(dev)
+    got = (flt(img.to(dev), specified_parameter=p.to(dev))[0] if clip else flt.run(img.to(dev), p.to(dev))).cpu()
+    assert torch.equal(torch.isnan(got), torch.isnan(ref)), O.OP_NAMES[op]
+    assert torch.equal(torch.isposinf(got), torch.isposinf(ref)) and torch.equal(torch.isneginf(got), torch.isneginf(ref))
+    fin = torch.isfinite(ref)
+    assert out_err(got[fin].numpy(), ref[fin].numpy()) <= OUT_ATOL, O.OP_NAMES[op]
+    assert int(torch.isnan(ref).sum()) >= 4      # the case really exercises the propagation
+
+
+def test_nan_batch_trips_the_pool_refill_guard(F, cfg, dev):
+    """train.py:374: `torch.isnan(retouch).any() or torch.isinf(retouch).any()` must be True for exactly
+    the batches for which the reference says so -- a NaN made by a singular CCM at step t and fed to
+    Tone / Gamma / S+ at step t+1 must survive."""
+    from adaptiveisp_b200 import functional as AF
+    img = cases.edge_image(2, 16, 16, seed=2, in_range=True)
+    p_ccm = torch.tensor([[1.0, -0.5, -0.5, 0.2, 0.5, 0.3, 0.1, 0.1, 0.8]]).repeat(2, 1)   # row 0 sums to 0
+    step1_ref = O.forward(O.OP_CCM, img, p_ccm)
+    step1 = cls_for(F, O.OP_CCM)(cfg).to(dev)(img.to(dev), specified_parameter=p_ccm.to(dev))[0]
+    assert torch.equal(torch.isnan(step1.cpu()), torch.isnan(step1_ref))
+    assert bool(torch.isnan(step1_ref).any())
+    for op in (O.OP_TONE, O.OP_GAMMA, O.OP_SATPLUS, O.OP_CONTRAST, O.OP_NLM):
+        _, p = cases.params_for(op, 2, seed=3)
+        ref = O.forward(op, step1_ref, p)
+        got = cls_for(F, op)(cfg).to(dev)(step1, specified_parameter=p.to(dev))[0].cpu()
+        bad_ref = bool(torch.isnan(ref).any() or torch.isinf(ref).any())
+        bad_got = bool(torch.isnan(got).any() or torch.isinf(got).any())
+        assert bad_ref and bad_got, O.OP_NAMES[op]
+        assert torch.equal(torch.isnan(got), torch.isnan(ref)), O.OP_NAMES[op]
+        down = AF.block_mean(got.to(dev), (4, 4))
+        assert not bool(AF.image_stats(down)[1].all())           # the one-pass guard sees it too
+
+
+# ----------------------------------------------------------------------------------------------
+# 5. USM: a tile whose 2-px halo leaves the image although the tile itself does not touch the frame
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size", [(1, 33, 260), (1, 49, 512), (2, 17, 384), (1, 34, 260), (1, 35, 516)])
+def test_usm_halo_leaves_image_on_tma_path(F, cfg, dev, size):
+    """H % 16 == 1 with W % 4 == 0 and W > 256: the last-but-one tile row ends one row short of the frame
+    while its halo row y0 + 17 == H is outside; reflect padding (isp/sharpen.py:76-78) must apply there
+    (the TMA path zero-fills out-of-bounds elements).  Forward, d/dsigma, d/damount and d/d img."""
+    B, H, W = size
+    flt = F.SharpenUSMFilter(cfg).to(dev)
+    img = cases.edge_image(B, H, W, seed=H, in_range=True)
+    p = torch.tensor([[1.1, 1.5], [0.6, 0.8]])[:B]
+    g = cases.grad_out(img.shape, H)
+    xc, pc = img.clone().requires_grad_(True), p.clone().requires_grad_(True)
+    yc = O.forward(O.OP_USM, xc, pc)
+    (yc * g).sum().backward()
+    xd, pd = img.to(dev).requires_grad_(True), p.to(dev).requires_grad_(True)
+    yd = flt(xd, specified_parameter=pd)[0]
+    (yd * g.to(dev)).sum().backward()
+    err = (yd.detach().cpu() - yc.detach()).abs()
+    assert float(err.max()) <= OUT_ATOL, f"worst row {int(err.amax(dim=(0, 1, 3)).argmax())} of {H}"
+    assert_grad(pd.grad.cpu().numpy(), pc.grad.numpy(), GRAD_RTOL, "USM d/d(sigma, amount)")
+    assert rel_err(xd.grad.cpu().numpy(), xc.grad.numpy()) <= GRAD_RTOL
+
+
+# ----------------------------------------------------------------------------------------------
+# 6. fused sequence backward, second generation: up to 6 stages, ColorFilter, strictness, identity
+# ----------------------------------------------------------------------------------------------
+def _chain_case(B, S, H, W, seed, pool, lens=None, fixed_first=None):
+    rng = np.random.RandomState(seed)
+    ops = rng.choice(pool, size=(B, S))
+    if fixed_first is not None:
+        ops[0, :len(fixed_first)] = fixed_first
+    if lens is None:
+        lens = rng.randint(1, S + 1, size=B)
+        lens[0] = S if fixed_first is None else len(fixed_first)
+    img = cases.edge_image(B, H, W, seed=seed, in_range=True)
+    P = torch.zeros((B, S, 24))
+    plist = [[None] * S for _ in range(B)]
+    for b in range(B):
+        for k in range(S):
+            _, p = cases.params_for(int(ops[b, k]), 1, seed=70 + 5 * b + k + seed)
+            plist[b][k] = p
+            P[b, k, :O.OP_NPARAMS[int(ops[b, k])]] = p.reshape(-1)
+    return ops, np.asarray(lens), img, P, plist
+
+
+@pytest.mark.parametrize("clip_each", [True, False])
+@pytest.mark.parametrize("S,size", [(5, (6, 40, 52)), (6, (4, 33, 47)), (6, (3, 64, 64)), (2, (3, 17, 23))])
+def test_fused_chain_up_to_six_stages_with_color(dev, clip_each, S, size):
+    """Sequences of up to AISP_MAX_CHAIN_BWD = 6 per-pixel filters (BASELINE configs[4] draws up to 5),
+    ColorFilter included, forward in one pass and backward in one pass: every stage's parameter
+    gradients and the image gradient against autograd through the CPU oracle.  (33x47 / 17x23: the
+    scalar cp.async path with a ragged tail; 64x64: exactly one 4096-pixel chunk.)"""
+    from adaptiveisp_b200 import functional as AF
+    B, H, W = size
+    ops, lens, img, P, plist = _chain_case(B, S, H, W, 31 + S, cases.POINTWISE_OPS,
+                                           fixed_first=[O.OP_COLOR, O.OP_TONE, O.OP_CCM, O.OP_COLOR][:min(S, 4)])
+    g = cases.grad_out(img.shape, 31)
+    xd = img.to(dev).requires_grad_(True)
+    Pd = P.to(dev).requires_grad_(True)
+    y = AF.apply_chain(xd, Pd, torch.tensor(ops, dtype=torch.int32, device=dev),
+                       torch.tensor(lens, dtype=torch.int32, device=dev), clip_each=clip_each)
+    (y * g.to(dev)).sum().backward()
+    # rounding compounds over the stages on BOTH sides (a gamma with p < 1 amplifies an upstream 1e-7 by
+    # up to p * 0.001^(p-1) ~ 30): the per-filter bars (1e-5 / 1e-4) are widened by the chain length
+    out_tol, grad_tol = 1e-5 * max(S, 3), 1e-4 * max(S, 3)
+    chk = Checks()
+    for b in range(B):
+        n = int(lens[b])
+        xc = img[b:b + 1].clone().requires_grad_(True)
+        pcs = [plist[b][k].clone().requires_grad_(True) for k in range(n)]
+        yc = O.chain([int(o) for o in ops[b, :n]], xc, pcs, clip_each)
+        (yc * g[b:b + 1]).sum().backward()
+        tag = f"sample {b} {[O.OP_NAMES[int(o)] for o in ops[b, :n]]}"
+        chk.out(y[b:b + 1].detach().cpu().numpy(), yc.detach().numpy(), out_tol, tag)
+        chk.norm(xd.grad[b:b + 1].cpu().numpy(), xc.grad.numpy(), grad_tol, tag + " d/d img")
+        for k in range(n):
+            m = O.OP_NPARAMS[int(ops[b, k])]
+            ref = pcs[k].grad.reshape(-1).numpy()
+            if np.abs(ref).max() > 1e-6:
+                chk.grad(Pd.grad[b, k, :m].cpu().numpy(), ref, grad_tol, f"{tag} stage {k}")
+        if n < S:
+            assert float(Pd.grad[b, n:].abs().max()) == 0.0
+    chk.done()
+
+
+def test_fused_chain_full_size_e_g_wb_ccm(dev):
+    """The chain of isp/filters.py:753-815 (E -> G -> WB -> CCM, the reference's own parameters) at the
+    bench size 64 x 512 x 512: fused forward and fused backward against the oracle on two images."""
+    from adaptiveisp_b200 import functional as AF
+    B, H, W = 64, 512, 512
+    img = cases.lod_batch(B, H, W, seed=1234)
+    ops = [O.OP_EXPOSURE, O.OP_GAMMA, O.OP_WB, O.OP_CCM]
+    P = torch.zeros((B, 4, 24))
+    P[:, 0, 0] = 0.09012079
+    P[:, 1, 0] = 0.38566995
+    P[:, 2, :3] = torch.tensor([2.4052505, 1.2233436, 1.8800205])
+    P[:, 3, :9] = torch.tensor([1.6, -0.4, -0.2, -0.3, 1.5, -0.2, -0.1, -0.5, 1.6])
+    P[:, 0, 0] += torch.linspace(-0.5, 1.5, B)               # per-sample exposure: dark and clipped frames
+    gen = torch.Generator(device=dev).manual_seed(5)
+    g = torch.randn((B, 3, H, W), device=dev, generator=gen)
+    Pd = P.to(dev).requires_grad_(True)
+    y = AF.apply_chain(img.to(dev), Pd, torch.tensor([ops] * B, dtype=torch.int32, device=dev), clip_each=True)
+    (y * g).sum().backward()
+    torch.cuda.synchronize()
+    chk = Checks()
+    for b in (3, 60):
+        pcs = [P[b:b + 1, k, :O.OP_NPARAMS[op]].clone().requires_grad_(True) for k, op in enumerate(ops)]
+        yc = O.chain(ops, img[b:b + 1], pcs, True)
+        (yc * g[b:b + 1].cpu()).sum().backward()
+        chk.out(y[b:b + 1].detach().cpu().numpy(), yc.detach().numpy(), 4e-5, f"image {b}")   # four stages
+        for k, op in enumerate(ops):
+            chk.grad(Pd.grad[b, k, :O.OP_NPARAMS[op]].cpu().numpy(), pcs[k].grad.reshape(-1).numpy(), 4e-4,
+                     f"image {b} stage {k} {O.OP_NAMES[op]}")
+    chk.done()
+
+
+def test_fused_chain_identity_none_and_strictness(dev):
+    """seq_len == 0 is the identity (gradient passes through), AISP_OP_NONE gives a zero image and zero
+    gradients, and -- the ops live on the device, nothing is read back -- a stencil op or an unknown
+    code inside a fused sequence poisons that sample with NaN instead of leaving stale memory."""
+    from adaptiveisp_b200 import AispError, functional as AF
+    B, S, H, W = 5, 3, 20, 24
+    img = cases.edge_image(B, H, W, seed=3, in_range=True)
+    ops = torch.tensor([[O.OP_GAMMA, O.OP_TONE, O.OP_WB],
+                        [O.OP_GAMMA, O.OP_TONE, O.OP_WB],
+                        [-1, O.OP_GAMMA, O.OP_GAMMA],
+                        [O.OP_SHARPEN, O.OP_GAMMA, O.OP_GAMMA],
+                        [O.OP_EXPOSURE, O.OP_NLM, O.OP_GAMMA]], dtype=torch.int32, device=dev)
+    lens = torch.tensor([3, 0, 3, 3, 3], dtype=torch.int32, device=dev)
+    P = torch.full((B, S, 24), 0.8, device=dev).requires_grad_(True)
+    x = img.to(dev).requires_grad_(True)
+    g = cases.grad_out(img.shape, 3).to(dev)
+    y = AF.apply_chain(x, P, ops, lens, clip_each=True)
+    (torch.nan_to_num(y) * g).sum().backward()
+    assert torch.equal(y[1], x[1].detach()) and torch.equal(x.grad[1], g[1])            # identity
+    assert float(P.grad[1].abs().max()) == 0.0
+    assert float(y[2].abs().max()) == 0.0 and float(x.grad[2].abs().max()) == 0.0       # AISP_OP_NONE
+    assert float(P.grad[2].abs().max()) == 0.0
+    for b in (3, 4):                                                                     # stencil op: NaN, not garbage
+        assert bool(torch.isnan(y[b]).all()) and bool(torch.isnan(x.grad[b]).all())
+        assert bool(torch.isnan(P.grad[b]).all())
+    assert bool(torch.isfinite(y[0]).all()) and bool(torch.isfinite(P.grad[0, :, 0]).all())
+    with pytest.raises(AispError):                                                       # 7 > AISP_MAX_CHAIN_BWD with grads
+        AF.apply_chain(x, torch.zeros((B, 7, 24), device=dev, requires_grad=True),
+                       torch.zeros((B, 7), dtype=torch.int32, device=dev))
+    y7 = AF.apply_chain(x.detach(), torch.zeros((B, 7, 24), device=dev), torch.zeros((B, 7), dtype=torch.int32, device=dev))
+    assert y7.shape == x.shape                                                           # forward-only: up to 8 steps

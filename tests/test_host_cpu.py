@@ -39,11 +39,11 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_library_metadata_calls(lib):
-    assert lib.aisp_version() == 2
+    assert lib.aisp_version() == 3
     for op in range(13):
         assert lib.aisp_op_num_params(op) == O.OP_NPARAMS[op]
     assert lib.aisp_op_num_params(99) == -1
-    assert lib.aisp_bwd_scratch_bytes(64, 512, 512) == 64 * 128 * 32 * 4 * 4    # x AISP_MAX_CHAIN_BWD
+    assert lib.aisp_bwd_scratch_bytes(64, 512, 512) == 64 * 128 * 32 * 4 * 6    # x AISP_MAX_CHAIN_BWD
     assert lib.aisp_bwd_scratch_bytes(0, 512, 512) == 0
     assert b"NULL" in lib.aisp_status_string(-1)
     # argument validation happens before any CUDA call, so it is checkable without a GPU
