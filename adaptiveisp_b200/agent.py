@@ -104,9 +104,15 @@ class Agent(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def downsample(self, x):
-        """agent.py:97.  Evenly dividing CUDA inputs that carry no gradient (the training case,
-        train.py:255) take the one-pass block-mean kernel; everything else the PyTorch module."""
+        """agent.py:97.  An image that left this Agent carries the block means its kernels emitted from
+        their store path (``_aisp_down``): the next step / the critic reuse them instead of re-reading
+        the full-resolution image.  Otherwise evenly dividing CUDA inputs that carry no gradient (the
+        training case, train.py:255) take the one-pass block-mean kernel; everything else the PyTorch
+        module."""
         oh, ow = self.down_sample.output_size
+        cached = getattr(x, "_aisp_down", None)
+        if cached is not None and cached.shape == (x.shape[0], 3, oh, ow) and cached.device == x.device:
+            return cached
         if x.is_cuda and not x.requires_grad and x.dtype == torch.float32 and x.is_contiguous() \
                 and x.shape[2] % oh == 0 and x.shape[3] % ow == 0 and x.shape[0] * 3 <= 65535:
             return AF.block_mean(x, (oh, ow))
@@ -176,11 +182,17 @@ class Agent(nn.Module):
             float(self.cfg.test_steps), float(self.cfg.early_stop_penalty))
         surrogate = torch.sum(hot * torch.log(pdf + 1e-10), dim=1, keepdim=True)
 
+        # ONE launch set applies the selected filter of every sample to the batch AND to its full-size
+        # twin (agent.py:155-157) and emits the 64x64 block means of the result from the store path (what
+        # the next step and the critic pool first, agent.py:97 / value.py:63)
         x_in = x
-        x = AF.apply_ops(x_in, rows, ops, clip=True, family=None)
-        high_res_output = None
-        if high_res is not None:
-            high_res_output = AF.apply_ops(high_res, rows, ops, clip=True, family=None)
+        oh, ow = self.down_sample.output_size
+        even = x_in.shape[2] % oh == 0 and x_in.shape[3] % ow == 0 and x_in.shape[0] * 3 <= 65535
+        if high_res is not None or even:
+            x, high_res_output, x_out_down = AF.apply_ops(x_in, rows, ops, clip=True, family=None, high_res=high_res,
+                                                          down_hw=(oh, ow) if even else None)
+        else:
+            x, high_res_output, x_out_down = AF.apply_ops(x_in, rows, ops, clip=True, family=None), None, None
 
         ones = self.filters[0].get_mask(x_in)
         filter_debug_info = [{"filter_parameters": f._debug(p), "mask": ones[0]}
@@ -206,7 +218,9 @@ class Agent(nn.Module):
         usage_penalty, early_stop_penalty = pens[:, 0:1], pens[:, 1:2]
 
         if self.cfg.clamp:
-            x = torch.clip(x, min=0.0, max=5.0)
+            x = torch.clip(x, min=0.0, max=5.0)       # a no-op on values: every kernel already clipped to [0,1]
+        if x_out_down is not None:
+            x._aisp_down = x_out_down                  # travels with the tensor object (see downsample)
         entropy_penalty = (1.0 - progress) * self.cfg.exploration_penalty * (-entropy + math.log(len(self.filters)))
         runtime_penalty = 0.0
         if self.cfg.filter_runtime_penalty:

@@ -7,7 +7,7 @@ cudaError_t launch_pointwise_fwd(const float*, float*, const float*, const int32
                                  int, BankMap, cudaStream_t);
 cudaError_t launch_pointwise_bank_fwd(const float*, float*, const float*, int, int, int, int, BankMap, cudaStream_t);
 cudaError_t launch_pointwise_bank_bwd(const float*, const float*, const float*, int, int, int, int, float*, float*, BankMap,
-                                      cudaStream_t);
+                                      bool, cudaStream_t);
 cudaError_t launch_pointwise_bwd(const float*, const float*, const float*, const int32_t*, int, int, int, int, float*,
                                  float*, float*, BankMap, cudaStream_t);
 cudaError_t launch_sharpen_fwd(const float*, float*, const float*, const int32_t*, int, int, int, BankMap, cudaStream_t);
@@ -25,6 +25,16 @@ cudaError_t launch_pointwise_chain_bwd(const float*, const float*, const float*,
 cudaError_t launch_select(const float*, const float*, int, int, const float*, const float*, const int32_t*, int, int, int,
                           float, float, long long*, long long*, int32_t*, float*, float*, float*, cudaStream_t);
 cudaError_t launch_select_bwd(const float*, const long long*, int, int, float*, cudaStream_t);
+cudaError_t launch_pointwise_seq_fwd(const float*, float*, const float*, const int32_t*, const int32_t*, int, int, int, int,
+                                     int, const float*, float*, int, int, float*, int, int, cudaStream_t);
+cudaError_t launch_sharpen_seq_fwd(const float*, float*, const float*, const int32_t*, const int32_t*, int, int, int, int,
+                                   int, const float*, float*, int, int, float*, int, int, cudaStream_t);
+cudaError_t launch_nlm_seq_fwd(const float*, float*, const float*, const int32_t*, const int32_t*, int, int, int, int, int,
+                               cudaStream_t);
+cudaError_t launch_block_mean_masked(const float*, float*, int, int, int, int, int, const int32_t*, const int32_t*, int, int,
+                                     cudaStream_t);
+bool pointwise_can_emit(int, int, int, int);
+bool sharpen_can_emit(int, int, int, int);
 int chain_bwd_max_steps();
 int pointwise_rows(int H, int W);
 int sharpen_rows(int H, int W);
@@ -206,6 +216,48 @@ int aisp_select_bwd(const float* grad_rows, const int64_t* sel, int B, int F, fl
     return (int)launch_select_bwd(grad_rows, (const long long*)sel, B, F, grad_packed_all, (cudaStream_t)stream);
 }
 
+// ---- sequence launch set: per-sample sequences with at most one stencil step, optional high-resolution
+// twin, optional block means of the output (see the header).  Every sample is processed by exactly one
+// of the three family kernels; no host knowledge of the ops is needed.
+int aisp_sequence_fwd(const float* img, float* out, const float* params, const int32_t* ops, const int32_t* seq_len,
+                      int B, int H, int W, int S, int clip_each, const float* hr_img, float* hr_out, int hr_H, int hr_W,
+                      float* down, int down_h, int down_w, float* nlm_dout_dh, float* nlm_wsum, void* stream) {
+    if (!img || !out || !params || !ops) return AISP_ERR_NULL;
+    if (!shape_ok(B, H, W) || S < 1 || S > AISP_MAX_STEPS) return AISP_ERR_SHAPE;
+    if (!al4(img) || !al4(out)) return AISP_ERR_ALIGN;
+    if (img == out) return AISP_ERR_UNSUPPORTED;
+    if ((hr_img == nullptr) != (hr_out == nullptr)) return AISP_ERR_NULL;
+    if (hr_img && (!shape_ok(B, hr_H, hr_W) || hr_img == hr_out)) return AISP_ERR_SHAPE;
+    if (down && (down_h <= 0 || down_w <= 0 || H % down_h || W % down_w || (long long)B * 3 > 65535)) return AISP_ERR_UNSUPPORTED;
+    if ((nlm_dout_dh || nlm_wsum) && S != 1) return AISP_ERR_UNSUPPORTED;   // closed-form d/dh needs NLM to be the whole step
+    cudaStream_t st = (cudaStream_t)stream;
+    const int flags = (clip_each & AISP_SEQ_CLIP);
+    // which families can emit the block means from their store path; the rest is completed by one masked pass
+    const bool pw_emit = down && pointwise_can_emit(H, W, down_h, down_w) && (((uintptr_t)img | (uintptr_t)out) & 15u) == 0;
+    const bool sh_emit = down && sharpen_can_emit(H, W, down_h, down_w);
+    cudaError_t e = launch_pointwise_seq_fwd(img, out, params, ops, seq_len, B, H, W, S, flags, hr_img, hr_out, hr_H, hr_W,
+                                             pw_emit ? down : nullptr, down_h, down_w, st);
+    if (e != cudaSuccess) return (int)e;
+    e = launch_sharpen_seq_fwd(img, out, params, ops, seq_len, B, H, W, S, flags, hr_img, hr_out, hr_H, hr_W,
+                               sh_emit ? down : nullptr, down_h, down_w, st);
+    if (e != cudaSuccess) return (int)e;
+    if (S == 1) {   // the select-apply case keeps the plain NLM kernel and its training stashes
+        e = launch_nlm_fwd(img, out, params, ops, B, H, W, nlm_dout_dh, nlm_wsum, plain_batch(), st);
+        if (e == cudaSuccess && hr_img)
+            e = launch_nlm_fwd(hr_img, hr_out, params, ops, B, hr_H, hr_W, nullptr, nullptr, plain_batch(), st);
+    } else {
+        e = launch_nlm_seq_fwd(img, out, params, ops, seq_len, B, H, W, S, flags, st);
+        if (e == cudaSuccess && hr_img)
+            e = launch_nlm_seq_fwd(hr_img, hr_out, params, ops, seq_len, B, hr_H, hr_W, S, flags, st);
+    }
+    if (e != cudaSuccess) return (int)e;
+    if (down) {
+        const int families = (pw_emit ? 0 : (1 << FAMILY_POINTWISE)) | (sh_emit ? 0 : (1 << FAMILY_SHARPEN)) | (1 << FAMILY_NLM);
+        e = launch_block_mean_masked(out, down, B, H, W, down_h, down_w, ops, seq_len, S, families, st);
+    }
+    return (int)e;
+}
+
 // ---- filter bank: F filters applied to the SAME batch (agent.py:103-107 runs every cfg.filter on
 // the input and stacks the results).  The op list is a HOST array; each family launches only over
 // its own slots (BankMap), so there are no idle CTAs and no device-side ops array.
@@ -257,9 +309,23 @@ int aisp_bank_bwd(const float* img, const float* grad_out, const float* params, 
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaSuccess;
-    if (m[FAMILY_POINTWISE].n)
-        e = launch_pointwise_bank_bwd(img, grad_out, params, B, H, W, clip ? 1 : 0, grad_params, (float*)scratch,
-                                      m[FAMILY_POINTWISE], st);
+    // the per-pixel slots go out in two launches: ColorFilter slots have their own instantiation
+    // (27 partial sums: see pw_bwd_kernel); cfg.filters holds none, so normally this is one launch
+    BankMap plain = m[FAMILY_POINTWISE], color = m[FAMILY_POINTWISE];
+    plain.n = color.n = 0;
+    plain.slots = color.slots = 0ull;
+    for (int j = 0; j < m[FAMILY_POINTWISE].n; ++j) {
+        const unsigned long long f = (m[FAMILY_POINTWISE].slots >> (4 * j)) & 15ull;
+        BankMap& t = (filter_ops[f] == AISP_OP_COLOR) ? color : plain;
+        t.slots |= f << (4 * t.n);
+        ++t.n;
+    }
+    if (plain.n)
+        e = launch_pointwise_bank_bwd(img, grad_out, params, B, H, W, clip ? 1 : 0, grad_params, (float*)scratch, plain,
+                                      false, st);
+    if (e == cudaSuccess && color.n)
+        e = launch_pointwise_bank_bwd(img, grad_out, params, B, H, W, clip ? 1 : 0, grad_params, (float*)scratch, color,
+                                      true, st);
     if (e == cudaSuccess && m[FAMILY_SHARPEN].n)
         e = launch_sharpen_bwd(img, grad_out, params, nullptr, B * m[FAMILY_SHARPEN].n, H, W, grad_params, nullptr,
                                nullptr, (float*)scratch, m[FAMILY_SHARPEN], st);

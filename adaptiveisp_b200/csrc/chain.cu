@@ -52,15 +52,15 @@ __host__ __device__ __forceinline__ int op_nacc(int op) {
     }
 }
 
-template <int NPX, bool GX, bool WITH_COLOR>
+template <int NPX, bool GX, bool WITH_COLOR, bool CLIP>
 __device__ __forceinline__ void bwd_step(int op, const float* __restrict__ c, const float (&R)[NPX],
                                          const float (&G)[NPX], const float (&B)[NPX], float (&gr)[NPX],
-                                         float (&gg)[NPX], float (&gb)[NPX], int clip, float* acc) {
+                                         float (&gg)[NPX], float (&gb)[NPX], float* acc) {
     switch (op) {
 #define AISP_CHAIN_CASE(OPC)                                                                         \
     case OPC: {                                                                                      \
         _Pragma("unroll") for (int i = 0; i < NPX; ++i)                                              \
-            PwBwd<OPC>::template px<GX>(c, R[i], G[i], B[i], gr[i], gg[i], gb[i], clip, acc);        \
+            PwBwd<OPC>::template px<GX, CLIP>(c, R[i], G[i], B[i], gr[i], gg[i], gb[i], acc);        \
         break;                                                                                       \
     }
         AISP_CHAIN_CASE(AISP_OP_EXPOSURE)
@@ -75,7 +75,7 @@ __device__ __forceinline__ void bwd_step(int op, const float* __restrict__ c, co
         if (WITH_COLOR) {
 #pragma unroll
             for (int i = 0; i < NPX; ++i)
-                PwBwd<AISP_OP_COLOR>::template px<GX>(c, R[i], G[i], B[i], gr[i], gg[i], gb[i], clip, acc);
+                PwBwd<AISP_OP_COLOR>::template px<GX, CLIP>(c, R[i], G[i], B[i], gr[i], gg[i], gb[i], acc);
         }
         break;
 #undef AISP_CHAIN_CASE
@@ -134,7 +134,7 @@ __device__ __forceinline__ int classify_sequence(const int32_t* __restrict__ ops
     return len;
 }
 
-template <int VEC, bool GIMG, int SMAX, int NACC>
+template <int VEC, bool GIMG, int SMAX, int NACC, bool CLIP>
 __global__ void __launch_bounds__(kThreads, NACC == 9 ? 2 : 1)
 pw_chain_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, const float* __restrict__ params,
                     const int32_t* __restrict__ ops, const int32_t* __restrict__ seq_len, int N, int S, int flags,
@@ -149,7 +149,6 @@ pw_chain_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gou
     __shared__ float red[kWarps * AISP_ACC_STRIDE];
     static_assert(SMAX <= kWarps, "one warp per step stages the constants");
     constexpr bool WITH_COLOR = (NACC == 27);
-    const int clip_each = flags & 1;
     const bool strict = (flags & 2) != 0;
     const int b = blockIdx.y;
     const int tid = threadIdx.x;
@@ -242,7 +241,7 @@ pw_chain_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gou
                         p[2 * kThreads] = make_float4(B[0], B[1], B[2], B[3]);
                     }
                     fwd_step<kChainPx, false>(sop[k], sc[k], R, G, B);
-                    if (clip_each) {
+                    if (CLIP) {
 #pragma unroll
                         for (int v = 0; v < kChainPx; ++v) { R[v] = clip01(R[v]); G[v] = clip01(G[v]); B[v] = clip01(B[v]); }
                     }
@@ -272,9 +271,9 @@ pw_chain_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gou
                         B[0] = d.x; B[1] = d.y; B[2] = d.z; B[3] = d.w;
                     }
                     if (k == 0 && !GIMG)
-                        bwd_step<kChainPx, false, WITH_COLOR>(sop[k], sc[k], R, G, B, gr, gg, gb, clip_each, acc[k]);
+                        bwd_step<kChainPx, false, WITH_COLOR, CLIP>(sop[k], sc[k], R, G, B, gr, gg, gb, acc[k]);
                     else
-                        bwd_step<kChainPx, true, WITH_COLOR>(sop[k], sc[k], R, G, B, gr, gg, gb, clip_each, acc[k]);
+                        bwd_step<kChainPx, true, WITH_COLOR, CLIP>(sop[k], sc[k], R, G, B, gr, gg, gb, acc[k]);
                 }
             }
             if (GIMG) {
@@ -352,12 +351,12 @@ chain_finalize_kernel(const float* __restrict__ partial, int nchunks, int S, int
 
 static inline bool aligned16c(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <int VEC, bool GIMG, int SMAX, int NACC>
+template <int VEC, bool GIMG, int SMAX, int NACC, bool CLIP>
 static cudaError_t launch_one(dim3 grid, cudaStream_t st, const float* img, const float* gout, const float* params,
                               const int32_t* ops, const int32_t* seq_len, int N, int S, int flags, int rounds,
                               int nchunks, float* gimg, float* partial) {
     constexpr size_t smem = (size_t)(2 * 6 + (SMAX - 1) * 3) * kThreads * sizeof(float4);
-    auto kern = pw_chain_bwd_kernel<VEC, GIMG, SMAX, NACC>;
+    auto kern = pw_chain_bwd_kernel<VEC, GIMG, SMAX, NACC, CLIP>;
     static bool attr_set_on[64] = {};   // per device: function attributes belong to the device's context
     int devi = 0;
     cudaGetDevice(&devi);
@@ -395,8 +394,12 @@ cudaError_t launch_pointwise_chain_bwd(const float* img, const float* gout, cons
     const dim3 grid((unsigned)nchunks, (unsigned)B), grid_color(1, (unsigned)B);
     const bool vec = (N % 4 == 0) && aligned16c(img) && aligned16c(gout) && (!grad_img || aligned16c(grad_img));
     cudaError_t e;
-#define AISP_LAUNCH(VEC, GIMG, SMAX, NACC, GRID) \
-    launch_one<VEC, GIMG, SMAX, NACC>(GRID, st, img, gout, params, ops, seq_len, (int)N, S, flags, rounds, nchunks, grad_img, partial)
+#define AISP_LAUNCH(VEC, GIMG, SMAX, NACC, GRID)                                                                   \
+    ((flags & AISP_SEQ_CLIP)                                                                                       \
+         ? launch_one<VEC, GIMG, SMAX, NACC, true>(GRID, st, img, gout, params, ops, seq_len, (int)N, S, flags, rounds, \
+                                                   nchunks, grad_img, partial)                                   \
+         : launch_one<VEC, GIMG, SMAX, NACC, false>(GRID, st, img, gout, params, ops, seq_len, (int)N, S, flags, rounds, \
+                                                    nchunks, grad_img, partial))
     if (vec) {
         if (S <= 4) e = grad_img ? AISP_LAUNCH(4, true, 4, 9, grid) : AISP_LAUNCH(4, false, 4, 9, grid);
         else        e = grad_img ? AISP_LAUNCH(4, true, kChainMax, 9, grid) : AISP_LAUNCH(4, false, kChainMax, 9, grid);

@@ -15,7 +15,7 @@
 //
 // When `dout_dh` is requested the same pass also accumulates sum(w*d) and sum(w*d*x), which give
 // d out / d h in closed form, so training never runs a second 121-shift pass.
-#include "aisp_common.cuh"
+#include "pointwise_math.cuh"   // fwd_px / stage_consts for the fused per-pixel prologue and epilogue (-fmad=false)
 
 namespace aisp {
 
@@ -81,18 +81,33 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
     return r;
 }
 
-template <bool WITH_GRAD, int LW>
+// SEQ: the sample's op SEQUENCE [per-pixel prologue] -> NLM -> [per-pixel epilogue] in one launch (params
+// [B,S,PSTRIDE], ops [B,S]): the prologue runs on every pixel as it is staged (tile + halo, wrapped
+// circularly: per-pixel filters commute with the wrap), the epilogue on the finished outputs in
+// registers.  SEQ == false is the plain single-filter kernel (ops [B], params [B,PSTRIDE]).
+template <bool WITH_GRAD, int LW, bool SEQ>
 __global__ void __launch_bounds__(kThreads, WITH_GRAD ? 3 : 4)
 nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __restrict__ dout_dh,
            float* __restrict__ wsum_out, const float* __restrict__ params, const int32_t* __restrict__ ops, int H,
-           int W, int x_off, BankMap bm) {
+           int W, int x_off, BankMap bm, const int32_t* __restrict__ seq_len, int S, int clip_each) {
     pdl_prologue();
     using Geo = NlmGeo<LW>;
     constexpr int kNlmSmH = Geo::SH, kNlmSmW = Geo::SW;
     __shared__ float sY[kNlmSmH][kNlmSmW];
     __shared__ float sC[3][kNlmSmH][kNlmSmW];
+    __shared__ float sraw[SEQ ? AISP_MAX_STEPS : 1][kConst];
+    __shared__ float ssc[SEQ ? AISP_MAX_STEPS : 1][kConst];
+    __shared__ int ssop[SEQ ? AISP_MAX_STEPS : 1];
     const int b = bank_sample(bm, blockIdx.z);   // filter-bank launches: see BankMap
-    if (sample_op(ops, bm, b) != AISP_OP_NLM) return;
+    int pos = 0, len = 1;
+    if (SEQ) {
+        len = seq_len ? min(max(seq_len[b], 0), S) : S;
+        pos = find_stencil(ops + (size_t)b * S, len, &len);
+        if (pos < 0 || ops[(size_t)b * S + pos] != AISP_OP_NLM) return;   // another family owns this sample
+        stage_consts(params, ops, b, S, len, sraw, ssc, ssop, bm);
+    } else {
+        if (sample_op(ops, bm, b) != AISP_OP_NLM) return;
+    }
     const int x0 = x_off + blockIdx.x * Geo::TW, y0 = blockIdx.y * Geo::TH;
     const size_t plane = (size_t)H * W;
     const float* src = img + (size_t)(b / bm.F) * 3 * plane;
@@ -110,9 +125,14 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
         for (int col = lane32; col < kNlmSmW; col += 32) {
             int gx = x0 - kNlmHalo + col;
             gx = wide ? (gx < 0 ? gx + W : (gx >= W ? gx - W : gx)) : wrap(gx, W);
-            const float r = clip01(__ldg(rp + gx));
-            const float g = clip01(__ldg(rp + plane + gx));
-            const float bl = clip01(__ldg(rp + 2 * plane + gx));
+            float r = __ldg(rp + gx), g = __ldg(rp + plane + gx), bl = __ldg(rp + 2 * plane + gx);
+            if (SEQ) {
+                for (int k = 0; k < pos; ++k) {
+                    fwd_px<true>(ssop[k], ssc[k], r, g, bl);
+                    if (clip_each) { r = clip01(r); g = clip01(g); bl = clip01(bl); }
+                }
+            }
+            r = clip01(r); g = clip01(g); bl = clip01(bl);
             sC[0][row][col] = r;
             sC[1][row][col] = g;
             sC[2][row][col] = bl;
@@ -123,7 +143,7 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
 
     const int lane = lane32 % LW;                               // column within the row group
     const int r0 = (warp * Geo::NG + lane32 / LW) * kNlmRows;   // first output row of this thread, relative to y0
-    const float h = params[(size_t)b * AISP_PSTRIDE];
+    const float h = params[((size_t)b * (SEQ ? S : 1) + pos) * AISP_PSTRIDE];
     const float hh = fmaxf(h, 0.f) + 1e-8f;              // relu(h) + EPS   (denoise.py:112)
     const float negk = -1.4426950408889634f / hh;        // exp(-d/hh) = 2^(d * negk)
 
@@ -158,19 +178,21 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
 
 #pragma unroll
         for (int dy = 5; dy >= -5; --dy) {
-            float d[kNlmRows + 4];
+            // 8 squared differences feed 4 five-high sums that share partial sums (12 FMA-pipe ops: one
+            // FMUL, eleven FFMA that each square-and-add).  The file is compiled with -fmad=false (the fused
+            // per-pixel prologue must round like ATen), so the multiply-adds are spelled out.
+            float t[kNlmRows + 4];
 #pragma unroll
-            for (int j = 0; j < kNlmRows + 4; ++j) {
-                const float t = yo[j] - ys[j + dy + 5];
-                d[j] = t * t;
-            }
-            // 5-high sums for the 4 rows, sharing partial sums
-            const float m34 = d[3] + d[4], a12 = d[1] + d[2], a56 = d[5] + d[6];
+            for (int j = 0; j < kNlmRows + 4; ++j) t[j] = yo[j] - ys[j + dy + 5];
+            const float m34 = fmaf(t[3], t[3], t[4] * t[4]);
+            const float c234 = fmaf(t[2], t[2], m34);
+            const float c2345 = fmaf(t[5], t[5], c234);
+            const float c345 = fmaf(t[5], t[5], m34);
             float v[kNlmRows];
-            v[0] = (d[0] + a12) + m34;
-            v[1] = (a12 + m34) + d[5];
-            v[2] = (d[2] + m34) + a56;
-            v[3] = m34 + (a56 + d[7]);
+            v[0] = fmaf(t[0], t[0], fmaf(t[1], t[1], c234));
+            v[1] = fmaf(t[1], t[1], c2345);
+            v[2] = fmaf(t[6], t[6], c2345);
+            v[3] = fmaf(t[7], t[7], fmaf(t[6], t[6], c345));
             // Rows are handled in pairs so that the adds / multiplies that do not touch the (row-
             // misaligned) RGB column run as Blackwell packed-fp32 instructions (FADD2 / FMUL2: two
             // lanes of work per issue slot -- the kernel is issue-bound, not FMA-pipe-bound).
@@ -227,17 +249,28 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
         if (gy >= H) continue;
         const float iw = 1.0f / wsum[i];
         if (wsum_out) wsum_out[sb * plane + (size_t)gy * W + gx] = wsum[i];
+        float yv[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            // 0 * x with the UNclipped centre pixel: the (1 - mask) * img term of the reference's lerp
-            // (isp/filters.py:115), NaN iff the input pixel is inf / NaN (an L2 hit: the tile was just staged)
-            const float y = fmaf(0.f, __ldg(src + (size_t)c * plane + (size_t)gy * W + gx), ac[c][i] * iw);
-            const size_t o = (size_t)b * 3 * plane + (size_t)c * plane + (size_t)gy * W + gx;
-            out[o] = clip01(y);
+            // 0 * x: the (1 - mask) * img term of the reference's lerp (isp/filters.py:115), NaN iff the
+            // filter's input pixel is inf / NaN.  Plain kernel: the UNclipped centre pixel (an L2 hit, the
+            // tile was just staged); after a fused prologue the staged (clipped) value stands in for it.
+            const float xin = (SEQ && pos > 0) ? sC[c][r0 + i + kNlmHalo][lane + kNlmHalo]
+                                               : __ldg(src + (size_t)c * plane + (size_t)gy * W + gx);
+            const float y = fmaf(0.f, xin, ac[c][i] * iw);
+            yv[c] = clip01(y);
             if (WITH_GRAD)
                 dout_dh[sb * 3 * plane + (size_t)c * plane + (size_t)gy * W + gx] =
                     pass01(y) * (bc[c][i] - y * wd[i]) * iw * inv_h2;
         }
+        if (SEQ) {
+            for (int k = pos + 1; k < len; ++k) {
+                fwd_px<true>(ssop[k], ssc[k], yv[0], yv[1], yv[2]);
+                if (clip_each) { yv[0] = clip01(yv[0]); yv[1] = clip01(yv[1]); yv[2] = clip01(yv[2]); }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) out[(size_t)b * 3 * plane + (size_t)c * plane + (size_t)gy * W + gx] = yv[c];
     }
 }
 
@@ -269,9 +302,11 @@ cudaError_t launch_finalize(const float* partial, int nrows, const float* params
                             int B, float* grad_params, BankMap bm, cudaStream_t st);
 int pointwise_rows(int H, int W);
 
-cudaError_t launch_nlm_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,
-                           float* dout_dh, float* wsum, BankMap bm, cudaStream_t st) {
-    // 28-wide tiles; a remainder of <= 12 columns goes to the half-warp layout (12 columns x 64 rows per CTA)
+// one NLM forward over [B,3,H,W]: 28-wide tiles, a remainder of <= 12 columns goes to the half-warp layout
+// (12 columns x 64 rows per CTA).  seq == true: per-sample sequences (see nlm_kernel<.., SEQ>).
+static cudaError_t launch_nlm_any(const float* img, float* out, const float* params, const int32_t* ops, int B, int H,
+                                  int W, float* dout_dh, float* wsum, BankMap bm, bool seq, const int32_t* seq_len,
+                                  int S, int clip_each, cudaStream_t st) {
     using G32 = NlmGeo<32>;
     using G16 = NlmGeo<16>;
     int n32 = W / G32::TW;
@@ -280,20 +315,41 @@ cudaError_t launch_nlm_fwd(const float* img, float* out, const float* params, co
     if (rem > 0 && !half) ++n32;
     if (n32 > 0) {
         dim3 grid(n32, (H + G32::TH - 1) / G32::TH, B);
-        if (dout_dh)
-            launch_pdl(nlm_kernel<true, 32>, grid, kThreads, st, img, out, dout_dh, wsum, params, ops, H, W, 0, bm);
+        if (seq)
+            launch_pdl(nlm_kernel<false, 32, true>, grid, kThreads, st, img, out, nullptr, nullptr, params, ops, H, W, 0, bm,
+                       seq_len, S, clip_each);
+        else if (dout_dh)
+            launch_pdl(nlm_kernel<true, 32, false>, grid, kThreads, st, img, out, dout_dh, wsum, params, ops, H, W, 0, bm,
+                       nullptr, 1, 0);
         else
-            launch_pdl(nlm_kernel<false, 32>, grid, kThreads, st, img, out, nullptr, wsum, params, ops, H, W, 0, bm);
+            launch_pdl(nlm_kernel<false, 32, false>, grid, kThreads, st, img, out, nullptr, wsum, params, ops, H, W, 0, bm,
+                       nullptr, 1, 0);
     }
     if (half) {
         dim3 grid(1, (H + G16::TH - 1) / G16::TH, B);
         const int x_off = n32 * G32::TW;
-        if (dout_dh)
-            launch_pdl(nlm_kernel<true, 16>, grid, kThreads, st, img, out, dout_dh, wsum, params, ops, H, W, x_off, bm);
+        if (seq)
+            launch_pdl(nlm_kernel<false, 16, true>, grid, kThreads, st, img, out, nullptr, nullptr, params, ops, H, W, x_off,
+                       bm, seq_len, S, clip_each);
+        else if (dout_dh)
+            launch_pdl(nlm_kernel<true, 16, false>, grid, kThreads, st, img, out, dout_dh, wsum, params, ops, H, W, x_off, bm,
+                       nullptr, 1, 0);
         else
-            launch_pdl(nlm_kernel<false, 16>, grid, kThreads, st, img, out, nullptr, wsum, params, ops, H, W, x_off, bm);
+            launch_pdl(nlm_kernel<false, 16, false>, grid, kThreads, st, img, out, nullptr, wsum, params, ops, H, W, x_off,
+                       bm, nullptr, 1, 0);
     }
     return cudaGetLastError();
+}
+
+cudaError_t launch_nlm_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,
+                           float* dout_dh, float* wsum, BankMap bm, cudaStream_t st) {
+    return launch_nlm_any(img, out, params, ops, B, H, W, dout_dh, wsum, bm, false, nullptr, 1, 0, st);
+}
+
+// per-sample sequences [prologue] -> NLM -> [epilogue] (no stashes: S > 1 has no closed-form d/dh)
+cudaError_t launch_nlm_seq_fwd(const float* img, float* out, const float* params, const int32_t* ops,
+                               const int32_t* seq_len, int B, int H, int W, int S, int clip_each, cudaStream_t st) {
+    return launch_nlm_any(img, out, params, ops, B, H, W, nullptr, nullptr, plain_batch(), true, seq_len, S, clip_each, st);
 }
 
 // ---------------------------------------------------------------------------------------------

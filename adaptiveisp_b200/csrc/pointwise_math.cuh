@@ -17,6 +17,23 @@ namespace aisp {
 // saturation filters, and the clamp backward of Filter.forward passes the gradient iff y <= 1: only
 // bit-identical forward arithmetic reproduces the reference's gradient mask on those pixels.
 // Explicit fmaf() is used only in gradient accumulators, where order is free.
+// Bare MUFU lg2 / ex2 (no denormal pre/post-scaling code around them): gamma only takes log2 of values
+// >= 0.001 and its exponent p * log2(x) stays far above -126, where these are bit-identical to
+// __log2f / exp2f and save four instructions per call.
+__device__ __forceinline__ float lg2_mufu(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_mufu(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// clamp backward as ATen does it (where(lo <= y <= hi, g, 0)): a select, so a non-finite upstream
+// gradient on a clipped pixel is dropped, not turned into NaN
+__device__ __forceinline__ float mask01(float y, float g) { return (y >= 0.f && y <= 1.f) ? g : 0.f; }
+
 __device__ __forceinline__ float lum_isp(float r, float g, float b) {  // isp/filters.py:12-14
     return (0.27f * r + 0.67f * g) + 0.06f * b;
 }
@@ -156,9 +173,9 @@ __device__ __forceinline__ void fwd_px(int op, const float* __restrict__ c, floa
     }
     case AISP_OP_GAMMA: {  // pow(max(x, 0.001), p) via lg2/ex2 (MUFU): |err| << 1e-5 on [0,1]
         const float p = c[0];
-        yr = exp2f(p * __log2f(max_nan(r, 0.001f)));   // torch.max(img, 0.001) keeps NaN
-        yg = exp2f(p * __log2f(max_nan(g, 0.001f)));
-        yb = exp2f(p * __log2f(max_nan(b, 0.001f)));
+        yr = ex2_mufu(p * lg2_mufu(max_nan(r, 0.001f)));   // torch.max(img, 0.001) keeps NaN
+        yg = ex2_mufu(p * lg2_mufu(max_nan(g, 0.001f)));
+        yb = ex2_mufu(p * lg2_mufu(max_nan(b, 0.001f)));
         break;
     }
     case AISP_OP_WB: {
@@ -251,14 +268,14 @@ template <int OP>
 struct PwBwd;
 
 #define AISP_MASK_CLIP(yr, yg, yb)                                   \
-    if (clip) { gr *= pass01(yr); gg *= pass01(yg); gb *= pass01(yb); }
+    if (CLIP) { gr = mask01(yr, gr); gg = mask01(yg, gg); gb = mask01(yb, gb); }
 
 template <>
 struct PwBwd<AISP_OP_EXPOSURE> {
     static constexpr int NACC = 1;
-    template <bool GIMG>
+    template <bool GIMG, bool CLIP>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
-                                              float& gb, int clip, float* acc) {
+                                              float& gb, float* acc) {
         const float s = c[0];
         AISP_MASK_CLIP(r * s, g * s, b * s)
         acc[0] = fmaf(gr, r, fmaf(gg, g, fmaf(gb, b, acc[0])));
@@ -269,13 +286,13 @@ struct PwBwd<AISP_OP_EXPOSURE> {
 template <>
 struct PwBwd<AISP_OP_GAMMA> {
     static constexpr int NACC = 1;
-    template <bool GIMG>
+    template <bool GIMG, bool CLIP>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
-                                              float& gb, int clip, float* acc) {
+                                              float& gb, float* acc) {
         const float p = c[0];
         const float xr = max_nan(r, 0.001f), xg = max_nan(g, 0.001f), xb = max_nan(b, 0.001f);
-        const float lr = __log2f(xr), lg = __log2f(xg), lb = __log2f(xb);
-        const float yr = exp2f(p * lr), yg = exp2f(p * lg), yb = exp2f(p * lb);
+        const float lr = lg2_mufu(xr), lg = lg2_mufu(xg), lb = lg2_mufu(xb);
+        const float yr = ex2_mufu(p * lr), yg = ex2_mufu(p * lg), yb = ex2_mufu(p * lb);
         AISP_MASK_CLIP(yr, yg, yb)
         acc[0] = fmaf(gr * yr, lr, fmaf(gg * yg, lg, fmaf(gb * yb, lb, acc[0])));  // x ln2 in finalize
         if (GIMG) {  // p * x^(p-1), only where the min-clamp passed (x >= 0.001, inclusive)
@@ -289,9 +306,9 @@ struct PwBwd<AISP_OP_GAMMA> {
 template <>
 struct PwBwd<AISP_OP_WB> {
     static constexpr int NACC = 3;
-    template <bool GIMG>
+    template <bool GIMG, bool CLIP>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
-                                              float& gb, int clip, float* acc) {
+                                              float& gb, float* acc) {
         AISP_MASK_CLIP(r * c[0], g * c[1], b * c[2])
         acc[0] = fmaf(gr, r, acc[0]); acc[1] = fmaf(gg, g, acc[1]); acc[2] = fmaf(gb, b, acc[2]);
         if (GIMG) { gr *= c[0]; gg *= c[1]; gb *= c[2]; }
@@ -301,9 +318,9 @@ struct PwBwd<AISP_OP_WB> {
 template <>
 struct PwBwd<AISP_OP_CCM> {
     static constexpr int NACC = 9;
-    template <bool GIMG>
+    template <bool GIMG, bool CLIP>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
-                                              float& gb, int clip, float* acc) {
+                                              float& gb, float* acc) {
         const float yr = (r * c[0] + g * c[1]) + b * c[2];
         const float yg = (r * c[3] + g * c[4]) + b * c[5];
         const float yb = (r * c[6] + g * c[7]) + b * c[8];
@@ -322,8 +339,8 @@ struct PwBwd<AISP_OP_CCM> {
 
 // one channel of a curve filter.  u_k = sat(8x - k) = 8 * clip(x - k/8, 0, 1/8) (see curve8);
 // accumulates g*u_k (8x the segment sums, undone in finalize_grads) and g*y.
-template <bool GIMG>
-__device__ __forceinline__ void curve8_bwd(float x, const float* c, int stride, float sc, float& g, int clip,
+template <bool GIMG, bool CLIP>
+__device__ __forceinline__ void curve8_bwd(float x, const float* c, int stride, float sc, float& g,
                                            float* acc, int astride, float& yacc) {
     float u[8], v[8];
     float sum = 0.f;
@@ -334,7 +351,7 @@ __device__ __forceinline__ void curve8_bwd(float x, const float* c, int stride, 
         sum = fmaf(u[k], c[k * stride], sum);
     }
     const float y = sum * (sc * 0.125f);
-    if (clip) g *= pass01(y);
+    if (CLIP) g = mask01(y, g);
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k * astride] = fmaf(g, u[k], acc[k * astride]);
     yacc = fmaf(g, y, yacc);
@@ -349,33 +366,33 @@ __device__ __forceinline__ void curve8_bwd(float x, const float* c, int stride, 
 template <>
 struct PwBwd<AISP_OP_TONE> {
     static constexpr int NACC = 9;
-    template <bool GIMG>
+    template <bool GIMG, bool CLIP>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
-                                              float& gb, int clip, float* acc) {
-        curve8_bwd<GIMG>(r, c, 1, c[8], gr, clip, acc, 1, acc[8]);
-        curve8_bwd<GIMG>(g, c, 1, c[8], gg, clip, acc, 1, acc[8]);
-        curve8_bwd<GIMG>(b, c, 1, c[8], gb, clip, acc, 1, acc[8]);
+                                              float& gb, float* acc) {
+        curve8_bwd<GIMG, CLIP>(r, c, 1, c[8], gr, acc, 1, acc[8]);
+        curve8_bwd<GIMG, CLIP>(g, c, 1, c[8], gg, acc, 1, acc[8]);
+        curve8_bwd<GIMG, CLIP>(b, c, 1, c[8], gb, acc, 1, acc[8]);
     }
 };
 
 template <>
 struct PwBwd<AISP_OP_COLOR> {
     static constexpr int NACC = 27;
-    template <bool GIMG>
+    template <bool GIMG, bool CLIP>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
-                                              float& gb, int clip, float* acc) {
-        curve8_bwd<GIMG>(r, c + 0, 3, c[24], gr, clip, acc + 0, 3, acc[24]);
-        curve8_bwd<GIMG>(g, c + 1, 3, c[25], gg, clip, acc + 1, 3, acc[25]);
-        curve8_bwd<GIMG>(b, c + 2, 3, c[26], gb, clip, acc + 2, 3, acc[26]);
+                                              float& gb, float* acc) {
+        curve8_bwd<GIMG, CLIP>(r, c + 0, 3, c[24], gr, acc + 0, 3, acc[24]);
+        curve8_bwd<GIMG, CLIP>(g, c + 1, 3, c[25], gg, acc + 1, 3, acc[25]);
+        curve8_bwd<GIMG, CLIP>(b, c + 2, 3, c[26], gb, acc + 2, 3, acc[26]);
     }
 };
 
 template <>
 struct PwBwd<AISP_OP_CONTRAST> {
     static constexpr int NACC = 1;
-    template <bool GIMG>
+    template <bool GIMG, bool CLIP>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
-                                              float& gb, int clip, float* acc) {
+                                              float& gb, float* acc) {
         const float p = c[0], ip = 1.f - p;
         const float l0 = lum_isp(r, g, b);
         const float l = clip01(l0);
@@ -402,9 +419,9 @@ struct PwBwd<AISP_OP_CONTRAST> {
 template <>
 struct PwBwd<AISP_OP_WNB> {
     static constexpr int NACC = 1;
-    template <bool GIMG>
+    template <bool GIMG, bool CLIP>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
-                                              float& gb, int clip, float* acc) {
+                                              float& gb, float* acc) {
         const float p = c[0], ip = 1.f - p;
         const float l = lum_isp(r, g, b);
         AISP_MASK_CLIP(ip * r + p * l, ip * g + p * l, ip * b + p * l)
@@ -421,9 +438,9 @@ struct PwBwd<AISP_OP_WNB> {
 template <>
 struct PwBwd<AISP_OP_SATPLUS> {
     static constexpr int NACC = 1;
-    template <bool GIMG>
+    template <bool GIMG, bool CLIP>
     static __device__ __forceinline__ void px(const float* c, float r0, float g0, float b0, float& gr, float& gg,
-                                              float& gb, int clip, float* acc) {
+                                              float& gb, float* acc) {
         const float p = c[0], ip = 1.f - p;
         const float r = clip01(r0), g = clip01(g0), b = clip01(b0);
         float fr, fg, fb;
@@ -480,6 +497,21 @@ struct PwBwd<AISP_OP_SATPLUS> {
         }
     }
 };
+
+// position of the (first) stencil step of sample b's sequence, or -1; *end = effective length (a
+// second stencil step ends the sequence: the host-side planner splits such sequences into phases)
+__device__ __forceinline__ int find_stencil(const int32_t* __restrict__ o, int len, int* end) {
+    int pos = -1;
+    *end = len;
+    for (int k = 0; k < len; ++k) {
+        const int op = o[k];
+        if (!is_pointwise(op)) {
+            if (pos < 0 && (is_sharpen(op) || op == AISP_OP_NLM)) pos = k;
+            else { *end = k; break; }
+        }
+    }
+    return pos;
+}
 
 // Bulk L2 prefetch of one CTA chunk of a 3-plane image (threads 0..2, one plane each): the rounds
 // after the first then see L2 latency instead of DRAM latency.  Needs 16-byte alignment (VEC == 4).

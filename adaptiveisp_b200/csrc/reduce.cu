@@ -9,14 +9,26 @@
 //
 // Thread <-> one output element; a warp covers 32 adjacent output columns, i.e. 32*bw contiguous
 // input floats per row (128-bit loads when bw % 4 == 0).  Read-only, 12 B/px.
-#include "aisp_common.cuh"
+#include "pointwise_math.cuh"   // find_stencil (sequence classification)
 
 namespace aisp {
 
+// `ops` != nullptr restricts the pass to the samples of some kernel families: `families` is a bit set over
+// (1 << FAMILY_*) of the sample's sequence (the family of its stencil step, FAMILY_POINTWISE without one) --
+// used to complete the block means that the per-pixel / sharpen kernels emitted from their store path
+// with the samples they could not serve (NLM: its 28-column tiles do not align with pooling blocks).
 __global__ void __launch_bounds__(kThreads)
 block_mean_kernel(const float* __restrict__ img, float* __restrict__ down, int H, int W, int oh, int ow, int bh,
-                  int bw, int vec) {
+                  int bw, int vec, const int32_t* __restrict__ ops, const int32_t* __restrict__ seq_len, int S,
+                  int families) {
     const int plane = blockIdx.z;                                   // b * 3 + c
+    if (ops) {
+        const int b = plane / 3;
+        int len = seq_len ? min(max(seq_len[b], 0), S) : S;
+        const int pos = find_stencil(ops + (size_t)b * S, len, &len);
+        const int fam = pos < 0 ? FAMILY_POINTWISE : (ops[(size_t)b * S + pos] == AISP_OP_NLM ? FAMILY_NLM : FAMILY_SHARPEN);
+        if (!((families >> fam) & 1)) return;
+    }
     const int ox = blockIdx.x * 32 + (threadIdx.x & 31);
     const int oy = blockIdx.y * kWarps + (threadIdx.x >> 5);
     if (ox >= ow || oy >= oh) return;
@@ -61,12 +73,17 @@ block_mean_kernel(const float* __restrict__ img, float* __restrict__ down, int H
     down[((size_t)plane * oh + oy) * ow + ox] = acc / (float)(bh * bw);
 }
 
-cudaError_t launch_block_mean(const float* img, float* down, int B, int H, int W, int oh, int ow, cudaStream_t st) {
+cudaError_t launch_block_mean_masked(const float* img, float* down, int B, int H, int W, int oh, int ow,
+                                     const int32_t* ops, const int32_t* seq_len, int S, int families, cudaStream_t st) {
     const int bh = H / oh, bw = W / ow;
     const int vec = ((bw & 3) == 0) && ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(img) & 15u) == 0);
     dim3 grid((ow + 31) / 32, (oh + kWarps - 1) / kWarps, B * 3);
-    block_mean_kernel<<<grid, kThreads, 0, st>>>(img, down, H, W, oh, ow, bh, bw, vec);
+    block_mean_kernel<<<grid, kThreads, 0, st>>>(img, down, H, W, oh, ow, bh, bw, vec, ops, seq_len, S, families);
     return cudaGetLastError();
+}
+
+cudaError_t launch_block_mean(const float* img, float* down, int B, int H, int W, int oh, int ow, cudaStream_t st) {
+    return launch_block_mean_masked(img, down, B, H, W, oh, ow, nullptr, nullptr, 1, 7, st);
 }
 
 }  // namespace aisp

@@ -19,7 +19,7 @@
 
 #include <cuda.h>  // CUtensorMap and enums only; cuTensorMapEncodeTiled is resolved through the runtime
 
-#include "aisp_common.cuh"
+#include "pointwise_math.cuh"   // fwd_px / stage_consts for the fused per-pixel prologue and epilogue (-fmad=false)
 
 namespace aisp {
 
@@ -328,6 +328,161 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, int tma_ok, const float
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Sequence forward: [per-pixel prologue] -> 3x3 sharpen / USM -> [per-pixel epilogue] in ONE launch
+// (the fixed chain of isp/filters.py:753-815, E -> G -> WB -> CCM -> Shr, and the replayed pipelines
+// of yolov3/val_adaptiveisp.py:291-327 whose sequence holds one stencil step).
+//   * the tile + halo lands in shared memory exactly as in sharpen_kernel (TMA, or the reflecting
+//     cp.async path); the prologue steps are then applied IN PLACE to the staged tile (halo included:
+//     per-pixel filters commute with the halo's coordinate map), 2720 staged pixels per 2048 outputs;
+//   * the stencil produces the thread's 3 x 2 x 4 outputs in registers, the epilogue steps run on
+//     those registers, and only the final values are stored: 24 B/px for the whole sequence;
+//   * two jobs per launch: the low-resolution batch and its high-resolution twin (same parameters,
+//     isp/filters.py:116-122, agent.py:155-157) are tiles of the same grid (blockIdx.x >= tiles of
+//     job 0 -> job 1, with its own tensor map);
+//   * EMIT: the 64x64 block means of job 0's OUTPUT (agent.py:97 / value.py:63 pool it next) leave
+//     through the store path: per-thread sums -> shared memory -> one thread per block, fixed order.
+// ---------------------------------------------------------------------------------------------
+struct SeqJob {
+    const float* img;
+    float* out;
+    int H, W;
+    int tiles_x, tiles;   // tiles per row / per image (tiles == 0: job absent)
+    int tma_ok, vec;
+};
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kThreads, 3)
+sharpen_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, SeqJob j0,
+                       SeqJob j1, const float* __restrict__ params, const int32_t* __restrict__ ops,
+                       const int32_t* __restrict__ seq_len, int S, int clip_each, float* __restrict__ down, int bh,
+                       int bw) {
+    pdl_prologue();
+    __shared__ __align__(128) float sm[kSmFloats];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ float raw[AISP_MAX_STEPS][kConst];
+    __shared__ float sc[AISP_MAX_STEPS][kConst];
+    __shared__ int sop[AISP_MAX_STEPS];
+    __shared__ float bs[EMIT ? 3 * kThreads : 1];
+    const int b = blockIdx.z;
+    int len = seq_len ? min(max(seq_len[b], 0), S) : S;
+    const int pos = find_stencil(ops + (size_t)b * S, len, &len);
+    if (pos < 0 || !is_sharpen(ops[(size_t)b * S + pos])) return;   // another family owns this sample
+    const bool second = (int)blockIdx.x >= j0.tiles;
+    const SeqJob& J = second ? j1 : j0;
+    const CUtensorMap* tmap = second ? &tmap1 : &tmap0;
+    const int tile = second ? (int)blockIdx.x - j0.tiles : (int)blockIdx.x;
+    const int H = J.H, W = J.W;
+    const int x0 = (tile % J.tiles_x) * kShTileW, y0 = (tile / J.tiles_x) * kShTileH;
+    const size_t base = (size_t)b * 3 * H * W;
+    const int op = ops[(size_t)b * S + pos];
+    const bool frame_tile = (x0 == 0) || (y0 == 0) || (x0 + kShTileW >= W) || (y0 + kShTileH >= H);
+    const bool usm_halo_out = (x0 < kHalo) || (y0 < kHalo) || (x0 + kShTileW + kHalo > W) || (y0 + kShTileH + kHalo > H);
+    const bool use_tma = J.tma_ok && !(op == AISP_OP_USM && usm_halo_out);
+    if (use_tma) {
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, kTmaBytes);
+            tma_load_3d(sm, tmap, x0 - kColOff, y0 - kHalo, b * 3, &bar);
+        }
+    } else {
+        stage_tile_cp(J.img + base, sm, H, W, x0, y0, J.vec != 0);
+    }
+    stage_consts(params, ops, b, S, len, raw, sc, sop, BankMap{1, 0, 0ull, 0ull});   // ends with a barrier
+    if (use_tma) mbar_wait(&bar, 0);
+    else cp_async_wait_all();
+    __syncthreads();
+
+    // prologue: steps 0 .. pos-1 on every staged pixel (tile + halo), in place
+    if (pos > 0) {
+        constexpr int kPlane = kSmH * kCpW;
+        for (int e = threadIdx.x; e < kPlane; e += kThreads) {
+            float r = sm[e], g = sm[kPlane + e], bl = sm[2 * kPlane + e];
+            for (int k = 0; k < pos; ++k) {
+                fwd_px<true>(sop[k], sc[k], r, g, bl);
+                if (clip_each) { r = clip01(r); g = clip01(g); bl = clip01(bl); }
+            }
+            sm[e] = r; sm[kPlane + e] = g; sm[2 * kPlane + e] = bl;
+        }
+        __syncthreads();
+    }
+
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int bx = tx * 4, by = ty * 2;
+    const int gx0 = x0 + bx, gy0 = y0 + by;
+    const bool vec_ok = J.vec && (gx0 + 3 < W);
+    const float* scs = sc[pos];
+    const float f = (op == AISP_OP_USM) ? scs[10] : scs[0];
+    float y[3][2][4];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float xc[2][4], blur[2][4], dblur[2][4];
+        const float* pl = sm + ch * kSmH * kCpW;
+        if (op == AISP_OP_USM)
+            block_blur<true, false, false, kCpW, kColOff>(pl, bx, by, scs, gx0, gy0, H, W, xc, blur, dblur);
+        else if (frame_tile)
+            block_blur<false, false, true, kCpW, kColOff>(pl, bx, by, scs, gx0, gy0, H, W, xc, blur, dblur);
+        else
+            block_blur<false, false, false, kCpW, kColOff>(pl, bx, by, scs, gx0, gy0, H, W, xc, blur, dblur);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                y[ch][r][i] = clip01(fmaf(0.f, xc[r][i], sharpen_value(op, xc[r][i], blur[r][i], f)));
+    }
+    // epilogue: steps pos+1 .. len-1 on the thread's own outputs
+    for (int k = pos + 1; k < len; ++k) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                fwd_px<true>(sop[k], sc[k], y[0][r][i], y[1][r][i], y[2][r][i]);
+                if (clip_each) { y[0][r][i] = clip01(y[0][r][i]); y[1][r][i] = clip01(y[1][r][i]); y[2][r][i] = clip01(y[2][r][i]); }
+            }
+    }
+    float psum[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int gy = gy0 + r;
+            if (gy >= H || gx0 >= W) continue;
+            const size_t off = base + ((size_t)ch * H + gy) * W + gx0;
+            if (vec_ok) {
+                stg_stream4(J.out + off, make_float4(y[ch][r][0], y[ch][r][1], y[ch][r][2], y[ch][r][3]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (gx0 + i < W) J.out[off + i] = y[ch][r][i];
+            }
+            if (EMIT) psum[ch] += (y[ch][r][0] + y[ch][r][1]) + (y[ch][r][2] + y[ch][r][3]);
+        }
+    if (EMIT) {
+        // (the host only asks for EMIT when W % bw == 0, H % bh == 0, bw % 4 == 0, bh % 2 == 0 and both
+        //  divide the tile: a thread's 4 x 2 outputs then lie in one pooling block, blocks in one tile)
+        if (second) return;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) bs[ch * kThreads + threadIdx.x] = psum[ch];
+        __syncthreads();
+        const int nbx = kShTileW / bw, nby = kShTileH / bh;      // pooling blocks per tile
+        const int tpb_x = bw / 4, tpb_y = bh / 2;                 // threads per block in x / y
+        const int ow = W / bw, oh = H / bh;
+        for (int e = threadIdx.x; e < 3 * nbx * nby; e += kThreads) {
+            const int ch = e / (nbx * nby), rem = e - ch * (nbx * nby);
+            const int pby = rem / nbx, pbx = rem - pby * nbx;
+            const int oy = y0 / bh + pby, ox = x0 / bw + pbx;
+            if (oy >= oh || ox >= ow) continue;
+            float s = 0.f;
+            for (int yy = 0; yy < tpb_y; ++yy)
+                for (int xx = 0; xx < tpb_x; ++xx)
+                    s += bs[ch * kThreads + (pby * tpb_y + yy) * 32 + pbx * tpb_x + xx];
+            down[(((size_t)b * 3 + ch) * oh + oy) * ow + ox] = s / (float)(bh * bw);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // transposed stencil: grad_img from the masked upstream gradient gy (staged by the kernel above)
 // CTA <-> (sample, 32x8 tile), one pixel per thread, all three planes.
@@ -474,6 +629,44 @@ cudaError_t launch_sharpen_fwd(const float* img, float* out, const float* params
     const int tma_ok = make_tile_map(&map, img, bm.n ? B / bm.n : B, H, W) ? 1 : 0;
     launch_pdl(sharpen_kernel<false, false>, grid, kThreads, st, map, tma_ok, img, nullptr, out, params, ops, H, W, vec,
                nullptr, bm);
+    return cudaGetLastError();
+}
+
+// Sequence forward over one or two jobs (job 1 = the high-resolution twin, hr_img == nullptr: absent).
+// down != nullptr: block means of job 0's output, when the pooling blocks tile the 128 x 16 CTA tile
+// (the caller checks with sharpen_can_emit and otherwise runs the stand-alone block-mean pass).
+bool sharpen_can_emit(int H, int W, int oh, int ow) {
+    if (oh <= 0 || ow <= 0 || H % oh || W % ow) return false;
+    const int bh = H / oh, bw = W / ow;
+    return (bw % 4 == 0) && (bh % 2 == 0) && (kShTileW % bw == 0) && (kShTileH % bh == 0);
+}
+
+cudaError_t launch_sharpen_seq_fwd(const float* img, float* out, const float* params, const int32_t* ops,
+                                   const int32_t* seq_len, int B, int H, int W, int S, int clip_each,
+                                   const float* hr_img, float* hr_out, int hr_H, int hr_W, float* down, int oh, int ow,
+                                   cudaStream_t st) {
+    CUtensorMap map0, map1;
+    SeqJob j0{}, j1{};
+    j0.img = img; j0.out = out; j0.H = H; j0.W = W;
+    j0.tiles_x = (W + kShTileW - 1) / kShTileW;
+    j0.tiles = j0.tiles_x * ((H + kShTileH - 1) / kShTileH);
+    j0.vec = ((W & 3) == 0) && al16(img) && al16(out);
+    j0.tma_ok = make_tile_map(&map0, img, B, H, W) ? 1 : 0;
+    memset(&map1, 0, sizeof(map1));
+    if (hr_img) {
+        j1.img = hr_img; j1.out = hr_out; j1.H = hr_H; j1.W = hr_W;
+        j1.tiles_x = (hr_W + kShTileW - 1) / kShTileW;
+        j1.tiles = j1.tiles_x * ((hr_H + kShTileH - 1) / kShTileH);
+        j1.vec = ((hr_W & 3) == 0) && al16(hr_img) && al16(hr_out);
+        j1.tma_ok = make_tile_map(&map1, hr_img, B, hr_H, hr_W) ? 1 : 0;
+    }
+    dim3 grid((unsigned)(j0.tiles + j1.tiles), 1, (unsigned)B);
+    if (down)
+        launch_pdl(sharpen_seq_fwd_kernel<true>, grid, kThreads, st, map0, map1, j0, j1, params, ops, seq_len, S, clip_each,
+                   down, H / oh, W / ow);
+    else
+        launch_pdl(sharpen_seq_fwd_kernel<false>, grid, kThreads, st, map0, map1, j0, j1, params, ops, seq_len, S,
+                   clip_each, nullptr, 1, 1);
     return cudaGetLastError();
 }
 

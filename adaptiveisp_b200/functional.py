@@ -54,10 +54,16 @@ def _ops_tensor(ops, B: int, device) -> torch.Tensor:
 
 
 class _ApplyOps(torch.autograd.Function):
-    """out[b] = [clip](process_{ops[b]}(img[b], P[b]))  with analytic backward in CUDA."""
+    """out[b] = [clip](process_{ops[b]}(img[b], P[b]))  with analytic backward in CUDA.
+
+    Optionally, in the same launch set (``aisp_sequence_fwd``): the high-resolution twin ``hr`` gets the same
+    op and parameters (no gradient: the reference only does this in evaluation, agent.py:155-157), and the
+    ``down_hw`` block means of ``out`` are produced from the kernels' store path (differentiable: the
+    gradient that reaches them -- the critic pools the retouched image, value.py:63 -- is folded into the
+    upstream gradient of ``out``)."""
 
     @staticmethod
-    def forward(ctx, img, P, ops, clip: bool, family: str):
+    def forward(ctx, img, P, ops, clip: bool, family: str, hr, down_hw):
         _lib.require_image(img, "img")
         B, _, H, W = img.shape
         if P.shape != (B, PSTRIDE) or not P.is_cuda or P.dtype != torch.float32:
@@ -72,8 +78,25 @@ class _ApplyOps(torch.autograd.Function):
         # (needed by the image-gradient kernel); rows of non-NLM samples are never touched
         stash = torch.empty_like(img) if (has_nlm and want_pgrad) else None
         wsum = torch.empty((B, 1, H, W), dtype=img.dtype, device=img.device) if (has_nlm and want_igrad) else None
+        hr_out = down = None
+        if hr is not None:
+            _lib.require_image(hr, "high_res")
+            if hr.shape[0] != B:
+                raise _lib.AispError("high_res must have the batch size of img")
+            hr_out = torch.empty_like(hr)
+        if down_hw is not None:
+            oh, ow = int(down_hw[0]), int(down_hw[1])
+            if H % oh or W % ow:
+                raise _lib.AispError(f"block means need evenly dividing sizes, got {H}x{W} -> {oh}x{ow}")
+            down = torch.empty((B, 3, oh, ow), dtype=torch.float32, device=img.device)
         with torch.cuda.device(img.device):
-            if family == FAMILY_POINTWISE:
+            if hr is not None or down is not None:
+                rc = L.aisp_sequence_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), ops.data_ptr(), None, B, H, W, 1,
+                                         int(clip), _lib.ptr(hr), _lib.ptr(hr_out),
+                                         hr.shape[2] if hr is not None else 0, hr.shape[3] if hr is not None else 0,
+                                         _lib.ptr(down), down.shape[2] if down is not None else 0,
+                                         down.shape[3] if down is not None else 0, _lib.ptr(stash), _lib.ptr(wsum), st)
+            elif family == FAMILY_POINTWISE:
                 rc = L.aisp_pointwise_fwd(img.data_ptr(), out.data_ptr(), P.data_ptr(), ops.data_ptr(), None,
                                           B, H, W, 1, int(clip), st)
             elif family == FAMILY_SHARPEN:
@@ -87,16 +110,24 @@ class _ApplyOps(torch.autograd.Function):
         _lib.check(rc, f"aisp {family} forward")
         ctx.save_for_backward(img, P, ops, stash, wsum, out if wsum is not None else None)
         ctx.clip = bool(clip)
-        ctx.family = family
-        return out
+        ctx.family = FAMILY_MIXED if (hr is not None or down is not None) else family
+        ctx.set_materialize_grads(False)
+        if hr_out is not None:
+            ctx.mark_non_differentiable(hr_out)
+        return out, hr_out, down
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _g_hr, g_down):
         img, P, ops, stash, wsum, out = ctx.saved_tensors
         B, _, H, W = img.shape
         need_img, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        if not (need_img or need_p):
-            return None, None, None, None, None
+        if not (need_img or need_p) or (g is None and g_down is None):
+            return None, None, None, None, None, None, None
+        if g_down is not None:
+            # d(block mean)/d(pixel) = 1 / (bh * bw): spread the pooled gradient over its block
+            bh, bw = H // g_down.shape[2], W // g_down.shape[3]
+            up = (g_down * (1.0 / (bh * bw))).repeat_interleave(bh, dim=2).repeat_interleave(bw, dim=3)
+            g = up if g is None else g + up
         g = g.contiguous()
         if g.dtype != torch.float32:
             raise _lib.AispError("grad_out must be float32")
@@ -129,20 +160,29 @@ class _ApplyOps(torch.autograd.Function):
                                              B, H, W, int(ctx.clip), _lib.ptr(stash), _lib.ptr(wsum), gP.data_ptr(),
                                              _lib.ptr(gimg), _lib.ptr(gy), sc.data_ptr(), sc.numel(), st)
         _lib.check(rc, f"aisp {family} backward")
-        return gimg, (gP if need_p else None), None, None, None
+        return gimg, (gP if need_p else None), None, None, None, None, None
 
 
-def apply_ops(img: torch.Tensor, P: torch.Tensor, ops, clip: bool, family: Optional[str] = None) -> torch.Tensor:
+def apply_ops(img: torch.Tensor, P: torch.Tensor, ops, clip: bool, family: Optional[str] = None,
+              high_res: Optional[torch.Tensor] = None, down_hw=None):
     """Apply ``ops[b]`` (int or int32 CUDA tensor ``[B]``) with packed parameters ``P[b]``.
 
     ``clip=True`` reproduces ``Filter.forward`` (isp/filters.py:115,125), ``clip=False``
     ``Filter.process`` / ``run`` (:138).  ``family`` narrows the launch to one kernel family when the
     caller knows the batch is homogeneous; ``None`` means heterogeneous ("mixed": three launches).
+
+    ``high_res`` ``[B,3,H2,W2]``: the full-size twin gets the same op and parameters in the same launch set
+    (isp/filters.py:116-122, agent.py:155-157).  ``down_hw`` ``(oh, ow)``: also return the block means of the
+    output (== ``nn.AdaptiveAvgPool2d`` for evenly dividing sizes), emitted from the kernels' store path.
+    With either, the result is ``(out, high_res_out | None, down | None)``; otherwise just ``out``.
     """
     if isinstance(ops, int) and family is None:
         family = family_of(ops)
     ops_t = _ops_tensor(ops, img.shape[0], img.device)
-    return _ApplyOps.apply(img, P, ops_t, clip, family or FAMILY_MIXED)
+    out, hr_out, down = _ApplyOps.apply(img, P, ops_t, clip, family or FAMILY_MIXED, high_res, down_hw)
+    if high_res is None and down_hw is None:
+        return out
+    return out, hr_out, down
 
 
 def apply_filter(img: torch.Tensor, param: torch.Tensor, op: int, clip: bool) -> torch.Tensor:
@@ -398,6 +438,43 @@ def chain_forward(img: torch.Tensor, P: torch.Tensor, ops: torch.Tensor, seq_len
                                            _lib.stream_ptr(img.device))
     _lib.check(rc, "aisp_pointwise_fwd")
     return out
+
+
+@torch.no_grad()
+def sequence_forward(img: torch.Tensor, P: torch.Tensor, ops: torch.Tensor, seq_len: Optional[torch.Tensor] = None,
+                     clip_each: bool = True, high_res: Optional[torch.Tensor] = None, down_hw=None):
+    """Per-sample op sequences with AT MOST ONE stencil step each (Shr / ShrV2 / USM / NLM, anywhere in the
+    sequence) in one launch set -- ``aisp_sequence_fwd``: per-pixel steps before the stencil step run on the
+    staged tile, steps after it on the outputs in registers, so a whole sequence costs one pass over HBM.
+    A second stencil step ends a sample's sequence (``replay.plan_pipeline`` splits such pipelines).
+
+    img ``[B,3,H,W]``; P ``[B,S,PSTRIDE]``; ops int32 ``[B,S]``; seq_len int32 ``[B]`` or None.
+    Returns ``(out, high_res_out | None, down | None)``."""
+    _lib.require_image(img, "img")
+    B, _, H, W = img.shape
+    S = ops.shape[1]
+    if not (1 <= S <= MAX_STEPS):
+        raise _lib.AispError(f"sequence length {S} outside 1..{MAX_STEPS}")
+    if P.shape != (B, S, PSTRIDE) or P.dtype != torch.float32 or not P.is_cuda:
+        raise _lib.AispError(f"P must be CUDA float32 [B,S,{PSTRIDE}]")
+    ops = _ops_tensor(ops, B, img.device)
+    if seq_len is not None:
+        seq_len = _ops_tensor(seq_len, B, img.device)
+    out = torch.empty_like(img)
+    hr_out = down = None
+    if high_res is not None:
+        _lib.require_image(high_res, "high_res")
+        hr_out = torch.empty_like(high_res)
+    if down_hw is not None:
+        down = torch.empty((B, 3, int(down_hw[0]), int(down_hw[1])), dtype=torch.float32, device=img.device)
+    with torch.cuda.device(img.device):
+        rc = _lib.lib().aisp_sequence_fwd(
+            img.data_ptr(), out.data_ptr(), P.contiguous().data_ptr(), ops.data_ptr(), _lib.ptr(seq_len), B, H, W, S,
+            int(clip_each), _lib.ptr(high_res), _lib.ptr(hr_out), high_res.shape[2] if high_res is not None else 0,
+            high_res.shape[3] if high_res is not None else 0, _lib.ptr(down), down.shape[2] if down is not None else 0,
+            down.shape[3] if down is not None else 0, None, None, _lib.stream_ptr(img.device))
+    _lib.check(rc, "aisp_sequence_fwd")
+    return out, hr_out, down
 
 
 @torch.no_grad()

@@ -23,11 +23,13 @@ from typing import Iterable, Iterator, Sequence, Tuple
 import torch
 
 
-def _static_grads(modules, step_fn, example_inputs, dev, warmup):
+def _static_grads(modules, step_fn, example_inputs, dev, warmup, bucket=False):
     """Warm `step_fn` up on a side stream, then give every parameter that received a gradient a
     STATIC zero ``.grad`` tensor (parameters that never get one -- ``fc_mask.*`` -- keep ``None``, as in the
     reference).  Captured with these in place, every graph ACCUMULATES into the same tensors on
-    replay, whichever slot it belongs to; callers clear them with ``zero_grad(set_to_none=False)``."""
+    replay, whichever slot it belongs to; callers clear them with ``zero_grad(set_to_none=False)``.
+    ``bucket=True``: the static gradients are views of ONE flat buffer (``dist.GradBucket``), so that a
+    data-parallel caller all-reduces them with a single NCCL call and no copies; returns the bucket."""
     for m in modules:
         m.zero_grad(set_to_none=True)
     side = torch.cuda.Stream(dev)
@@ -36,6 +38,11 @@ def _static_grads(modules, step_fn, example_inputs, dev, warmup):
         for _ in range(max(1, warmup)):
             step_fn(*example_inputs)
     torch.cuda.current_stream(dev).wait_stream(side)
+    if bucket:
+        from .dist import GradBucket
+        b = GradBucket([p for m in modules for p in m.parameters()], only_with_grad=True)
+        b.zero()
+        return b
     static = []
     for m in modules:
         for p in m.parameters():
@@ -200,9 +207,14 @@ class GraphedStep:
         out = g(x_new, z_new, states_new)       # copies into the static inputs, replays, returns static outputs
     """
 
-    def __init__(self, step_fn, example_inputs, modules=(), warmup: int = 2):
+    def __init__(self, step_fn, example_inputs, modules=(), warmup: int = 2, grad_bucket: bool = False):
         dev = example_inputs[0].device
-        self.static_grads = _static_grads(modules, step_fn, example_inputs, dev, warmup)
+        self.bucket = None
+        if grad_bucket:
+            self.bucket = _static_grads(modules, step_fn, example_inputs, dev, warmup, bucket=True)
+            self.static_grads = [self.bucket.flat]
+        else:
+            self.static_grads = _static_grads(modules, step_fn, example_inputs, dev, warmup)
         self.inputs = tuple(t.clone() for t in example_inputs)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):

@@ -29,9 +29,7 @@ class Phase:
     ops: torch.Tensor                 # int32 [B,S]
     seq_len: torch.Tensor             # int32 [B]   (0 = sample idle in this phase: copied through)
     params: torch.Tensor              # fp32  [B,S,PSTRIDE]
-    stencil_ops: Optional[torch.Tensor] = None   # int32 [B] (-1 = none) when any sample runs a stencil
-    stencil_params: Optional[torch.Tensor] = None
-    has_sharpen: bool = False
+    has_sharpen: bool = False         # informational: which stencil families appear in the phase
     has_nlm: bool = False
 
 
@@ -39,24 +37,22 @@ class Phase:
 class PipelinePlan:
     batch: int
     phases: List[Phase] = field(default_factory=list)
-    launches: int = 0
+    launches: int = 0                 # kernel launches with work (idle family launches exit at once)
 
 
 def segment(ops: Sequence[int]) -> List[List[int]]:
-    """Indices of one sample's steps grouped into fused segments: maximal runs of per-pixel ops
-    (at most MAX_STEPS long) and single stencil ops."""
-    out, cur = [], []
+    """Indices of one sample's steps grouped into fused segments: a segment holds per-pixel steps and AT
+    MOST ONE stencil step (anywhere in it) and is at most MAX_STEPS long -- what one
+    ``aisp_sequence_fwd`` call runs in a single pass over HBM.  A second stencil step opens a new segment
+    (its halo would need the first stencil's output at neighbouring pixels)."""
+    out, cur, has_stencil = [], [], False
     for k, op in enumerate(ops):
-        if op in AF.POINTWISE:
-            cur.append(k)
-            if len(cur) == MAX_STEPS:
-                out.append(cur)
-                cur = []
-        else:
-            if cur:
-                out.append(cur)
-                cur = []
-            out.append([k])
+        stencil = op not in AF.POINTWISE
+        if cur and (len(cur) == MAX_STEPS or (stencil and has_stencil)):
+            out.append(cur)
+            cur, has_stencil = [], False
+        cur.append(k)
+        has_stencil = has_stencil or stencil
     if cur:
         out.append(cur)
     return out
@@ -74,53 +70,43 @@ def plan_pipeline(steps: Sequence[Sequence[int]], params: Sequence[Sequence[torc
         ops_h = torch.zeros((B, S), dtype=torch.int32)
         len_h = torch.zeros((B,), dtype=torch.int32)
         P_h = torch.zeros((B, S, PSTRIDE), dtype=torch.float32)
-        st_h = torch.full((B,), -1, dtype=torch.int32)
+        fam = set()
         for b in range(B):
             if p >= len(segs[b]):
                 continue
+            f = AF.FAMILY_POINTWISE
             for j, k in enumerate(segs[b][p]):
                 op = int(steps[b][k])
                 ops_h[b, j] = op
                 P_h[b, j, :AF.NUM_PARAMS[op]] = params[b][k].detach().reshape(-1).float().cpu()
+                if op not in AF.POINTWISE:
+                    f = AF.family_of(op)
             len_h[b] = len(segs[b][p])
-            first = int(ops_h[b, 0])
-            if first not in AF.POINTWISE:
-                st_h[b] = first
+            fam.add(f)
         ph = Phase(ops=ops_h.to(device), seq_len=len_h.to(device), params=P_h.to(device))
-        ph.has_sharpen = bool(sum(int(v) in AF.SHARPEN for v in st_h.tolist()))
-        ph.has_nlm = bool(sum(int(v) == AF.OP_NLM for v in st_h.tolist()))
-        if ph.has_sharpen or ph.has_nlm:
-            ph.stencil_ops = st_h.to(device)
-            ph.stencil_params = P_h[:, 0, :].contiguous().to(device)
+        ph.has_sharpen = AF.FAMILY_SHARPEN in fam
+        ph.has_nlm = AF.FAMILY_NLM in fam
         plan.phases.append(ph)
-        plan.launches += 1 + int(ph.has_sharpen) + int(ph.has_nlm)
+        plan.launches += max(1, len(fam))
     return plan
 
 
 @torch.no_grad()
-def execute_plan(img: torch.Tensor, plan: PipelinePlan, clip_each: bool = True) -> torch.Tensor:
-    """Run a planned batch of pipelines: per phase one heterogeneous per-pixel launch (samples led by a
-    stencil op are skipped there) plus one launch per stencil family present in the phase."""
+def execute_plan(img: torch.Tensor, plan: PipelinePlan, clip_each: bool = True,
+                 high_res: Optional[torch.Tensor] = None):
+    """Run a planned batch of pipelines: one sequence launch set per phase (``aisp_sequence_fwd``: the
+    per-pixel, sharpen and NLM kernels back to back, each sample served by exactly one of them; samples
+    that already finished are carried through unchanged).  With ``high_res`` the same pipelines are
+    applied to the full-size twins in the same launches and ``(out, high_res_out)`` is returned."""
     _lib.require_image(img, "img")
     if img.shape[0] != plan.batch:
         raise _lib.AispError(f"plan was made for batch {plan.batch}, got {img.shape[0]}")
     if not plan.phases:
-        return img.clone()
-    L = _lib.lib()
-    B, _, H, W = img.shape
-    x = img
+        return img.clone() if high_res is None else (img.clone(), high_res.clone())
+    x, hr = img, high_res
     for ph in plan.phases:
-        nxt = AF.chain_forward(x, ph.params, ph.ops, ph.seq_len, clip_each, strict=False)
-        st = _lib.stream_ptr(img.device)
-        with torch.cuda.device(img.device):
-            if ph.has_sharpen:
-                _lib.check(L.aisp_sharpen_fwd(x.data_ptr(), nxt.data_ptr(), ph.stencil_params.data_ptr(),
-                                              ph.stencil_ops.data_ptr(), B, H, W, st), "aisp_sharpen_fwd")
-            if ph.has_nlm:
-                _lib.check(L.aisp_nlm_fwd(x.data_ptr(), nxt.data_ptr(), ph.stencil_params.data_ptr(),
-                                          ph.stencil_ops.data_ptr(), B, H, W, None, None, st), "aisp_nlm_fwd")
-        x = nxt
-    return x
+        x, hr, _ = AF.sequence_forward(x, ph.params, ph.ops, ph.seq_len, clip_each, high_res=hr)
+    return x if high_res is None else (x, hr)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -58,6 +58,10 @@ class DeviceReplayPool:
         self._live: List[int] = []                       # slots holding a record
         self._free: List[int] = list(range(self.capacity))
         self.h2d_bytes = 0
+        # fresh frames are uploaded on a side stream into a staging buffer: the PCIe copy overlaps whatever
+        # the compute stream is still running (the step that was just enqueued) and only the device-side
+        # scatter into the pool waits for it
+        self._h2d = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
         self.fill()
 
     # ------------------------------------------------------------------------------------------
@@ -73,7 +77,16 @@ class DeviceReplayPool:
                 raise ValueError("fetch_fresh(n) must return n images and n meta records")
             slots = [self._free.pop() for _ in range(n)]
             idx = torch.tensor(slots, dtype=torch.long, device=self.device)
-            src = imgs.to(self.device, dtype=torch.float32, non_blocking=True)
+            if self._h2d is not None:
+                with torch.cuda.stream(self._h2d):
+                    src = imgs.to(self.device, dtype=torch.float32, non_blocking=True)
+                    landed = torch.cuda.Event()
+                    landed.record(self._h2d)
+                cur = torch.cuda.current_stream(self.device)
+                cur.wait_event(landed)
+                src.record_stream(cur)
+            else:
+                src = imgs.to(self.device, dtype=torch.float32)
             self.h2d_bytes += imgs.numel() * imgs.element_size()
             self.images.index_copy_(0, idx, src)
             self.states.index_fill_(0, idx, 0.0)

@@ -40,21 +40,34 @@ B_PER_GPU, H, W = 64, 512, 512
 WORKLOAD = "configs[1]: full filter set (10 cfg.filters) fwd+bwd, batch=64 x 512x512 per GPU, synthetic LOD-shaped"
 METRIC = "isp_chain_megapixels_per_sec_fwd_bwd"
 ALGO_BYTES_FWD, ALGO_BYTES_BWD = 24, 24  # B/px, SURVEY.md §8(d): fwd r12+w12, bwd (param grads) r12+r12
+FILTER_NAMES = ["E", "G", "CCM", "Shr", "NLM", "T", "Ct", "S+", "BW", "W"]   # cfg.filters order (config.py:19-22)
+
+
+def bench_config(world):
+    """`config` of the JSON line -- identical for both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "height": H, "width": W, "filters": FILTER_NAMES,
+            "l2": "per step and GPU: 201 MB image, 2.0 GB of upstream gradients (one per filter) read, 2.0 GB "
+                  "output stack written -- far beyond the 126 MB L2; no flush",
+            "parallelism": f"dp{world} (batch-sharded replicas, no collective in the ISP path)"}
 
 
 # per-launch DRAM traffic measured by ncu (--set full) at this workload, profiles/r01_ncu_summary.txt
 NCU_TRAFFIC_BYTES = {"NLM": 550.5e6, "pw_fwd": 352.9e6, "pw_bwd": 410.6e6, "sharpen_fwd": 355.2e6, "sharpen_bwd": 407.2e6}
 # SASS instructions per (pixel, shift) of nlm_kernel<grad>'s main loop (993 per 44, cuobjdump) and lane use
-NLM_INSTR_PER_PXSHIFT, NLM_LANE_EFF = 993.0 / 44.0, 28.0 / 32.0
+NLM_INSTR_PER_PXSHIFT, NLM_LANE_EFF = 959.0 / 44.0, 28.0 / 32.0
 
 
 def nlm_issue_bound(fwd_ms, npx, sm_mhz):
     """NLM against the bound that actually limits it: warp-instruction issue (4 per clock per SM)."""
     thread_instr = npx * 121 * NLM_INSTR_PER_PXSHIFT / NLM_LANE_EFF
     ideal_ms = thread_instr / (148 * 128 * sm_mhz * 1e6) * 1e3
+    # SURVEY 8(d)'s bound for this kernel: >= 121 sqrt + 121 exp per pixel on 16 MUFU lanes per SM and clock
+    mufu_ms = npx * 242.0 / (148 * 16 * sm_mhz * 1e6) * 1e3
     return {"ideal_ms_at_full_issue_rate": round(ideal_ms, 3), "measured_ms": round(fwd_ms, 3),
             "frac": round(ideal_ms / fwd_ms, 3), "sm_mhz": sm_mhz,
-            "model": "B*H*W*121 shifts * 22.6 SASS instr / (28/32 lanes) / (148 SMs * 128 thread-instr/clk)"}
+            "mufu_bound_ms": round(mufu_ms, 3), "frac_of_mufu_bound": round(mufu_ms / fwd_ms, 3),
+            "model": "B*H*W*121 shifts * 21.8 SASS instr / (28/32 lanes) / (148 SMs * 128 thread-instr/clk); "
+                     "MUFU bound: 242 MUFU ops per pixel / (148 SMs * 16 lanes/clk)"}
 
 
 def clk_mhz(clocks):
@@ -145,31 +158,153 @@ def cpu_step(sample_b, reps):
 
 
 def run_reference(args):
+    """The reference's own CPU path (oracle port: the same ATen op sequence) on the host cores: exactly
+    --warmup untimed and --steps timed steps, each a bounded sample of the workload (`sample_b` of the 64
+    frames, sized so that the default run ends within a few minutes: ~2.5 s per step on 16 cores)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_b = 8  # bounded sample: 8 of the 64 frames per step (about 2-3 s of CPU work per step)
-    times = []
-    for _ in range(args.warmup if args.warmup < 2 else 1):
+    sample_b = 8 if args.steps <= 60 else 2
+    for _ in range(args.warmup):
         cpu_step(sample_b, 1)
-    steps = max(1, min(args.steps, 5))
-    for _ in range(steps):
+    times = []
+    for _ in range(args.steps):
         mps, dt, cores = cpu_step(sample_b, 1)
         times.append(dt)
     dt = sum(times) / len(times)
     value = 10 * sample_b * H * W / 1e6 / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU PyTorch path of the reference (oracle port, same ATen ops), "
-                                                 f"each step a bounded sample of {sample_b} frame(s) of the batch"},
+        "config": bench_config(max(1, args.gpus)),
+        "note": "CPU PyTorch path of the reference (oracle port, same ATen ops) on rank 0's host cores; each step is a "
+                f"bounded sample of {sample_b} of the {B_PER_GPU} frames, normalised per pixel",
         "cpu_baseline": {"value": value, "unit": "MP/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample_b} of 64 frames, 10 filters fwd+bwd, {steps} step(s) averaged"},
+                         "sample": f"{sample_b} of 64 frames, 10 filters fwd+bwd, {args.steps} step(s) averaged"},
         "e2e": {"value": value, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# PCIe roofline of the end-to-end path: pinned host <-> device copy rates with ALL ranks copying at once
+# ----------------------------------------------------------------------------------------------
+def pcie_probe(dev, world, barrier, dist, nbytes, reps=4):
+    """Per-rank GB/s of a 201 MB pinned copy: host->device alone, device->host alone, and both directions
+    at once on two streams (what the e2e loop does); every rank runs the same copy between barriers, the
+    slowest rank's rate is kept (and the sum over ranks: the box's aggregate)."""
+    n = nbytes // 4
+    h1 = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    h2 = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    d1, d2 = torch.empty(n, device=dev), torch.empty(n, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def h2d():
+        with torch.cuda.stream(s1):
+            d1.copy_(h1, non_blocking=True)
+
+    def d2h():
+        with torch.cuda.stream(s2):
+            h2.copy_(d2, non_blocking=True)
+
+    def both():
+        h2d()
+        d2h()
+
+    out = {}
+    for name, fn in (("h2d", h2d), ("d2h", d2h), ("duplex_per_dir", both)):
+        fn()
+        torch.cuda.synchronize(dev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize(dev)
+        gbs = nbytes * reps / 1e9 / (time.perf_counter() - t0)
+        t = torch.tensor([gbs, -gbs], device=dev)
+        if world > 1:
+            lo = t.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            out[name + "_GBs_min_rank"] = round(float(lo[0]), 2)
+            out[name + "_GBs_sum_ranks"] = round(float(t[0]), 2)
+        else:
+            out[name + "_GBs_min_rank"] = out[name + "_GBs_sum_ranks"] = round(gbs, 2)
+    out["bytes"] = nbytes
+    out["ranks_copying_concurrently"] = world
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# N > 1: BASELINE configs[2] where it belongs -- 5-step Agent rollout at B = 8 per rank (CUDA graph, nets +
+# selection + heterogeneous ISP apply + backward) followed by the data-parallel gradient all-reduce of the
+# real Agent + Value parameter set over NCCL (train.py:341-346), gradients living in one flat bucket
+# ----------------------------------------------------------------------------------------------
+def rollout_allreduce_section(dev, world, barrier, dist, iters=10):
+    from adaptiveisp_b200.agent import Agent
+    from adaptiveisp_b200.config import make_cfg
+    from adaptiveisp_b200.pipeline import GraphedStep
+    from adaptiveisp_b200.synthetic import lod_batch
+    from adaptiveisp_b200.value import Value
+    cfg = make_cfg()
+    B3 = 8
+    rank = int(os.environ.get("RANK", "0"))
+    torch.manual_seed(1234)                                    # same weights on every rank
+    agent = Agent(cfg, shape=(16, 64, 64), device=dev).to(dev).train()
+    value = Value(cfg, shape=(19, 64, 64)).to(dev).train()
+    x0 = lod_batch(B3, H, W, seed=1236 + rank, device=dev)
+    z = torch.rand((B3, cfg.z_dim), device=dev)
+    s0 = torch.zeros((B3, cfg.num_state_dim), device=dev)
+    g3 = torch.randn_like(x0)
+
+    def rollout_train(x, zz, states):
+        # five train.py:234-381-style iterations on the same images: state carried, each step's input is the
+        # previous retouch re-entering as a leaf (train.py:378-381); the critic scores input and retouch
+        for _ in range(cfg.test_steps):
+            (xo, ns, sur, pen), _dbg, _ = agent((x, zz, states), 0.5)
+            old_v, new_v = value(x, states), value(xo, ns)
+            loss = (xo * g3).sum() * 1e-6 + sur.sum() + pen.sum() + ((new_v.detach() - old_v) ** 2).mean() - new_v.mean()
+            loss.backward()
+            x, states = xo.detach(), ns.detach()
+        return x, states
+
+    gt = GraphedStep(rollout_train, (x0, z, s0), modules=[agent, value], grad_bucket=True)
+    bucket = gt.bucket
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(iters)]
+    for _ in range(3):
+        bucket.zero()
+        gt(x0, z, s0)
+        bucket.allreduce(average=True)
+        bucket.clip_grad_norm_(1e-5)
+    barrier()
+    for it in range(iters):
+        bucket.zero()
+        ev[it][0].record()
+        gt(x0, z, s0)
+        ev[it][1].record()
+        bucket.allreduce(average=True)                 # one NCCL call on the buffer backward wrote in place
+        ev[it][2].record()
+        bucket.clip_grad_norm_(1e-5)
+        ev[it][3].record()
+    barrier()
+    seg = [sum(e[k].elapsed_time(e[k + 1]) for e in ev) / iters for k in range(3)]
+    t = torch.tensor(seg + [sum(seg)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    seg = [float(v) for v in t]
+    nbytes = bucket.nbytes
+    res = {"batch_per_rank": B3, "steps": int(cfg.test_steps), "ranks": world,
+           "rollout_graph_ms": round(seg[0], 3), "allreduce_ms": round(seg[1], 4), "clip_ms": round(seg[2], 4),
+           "total_ms": round(seg[3], 3), "allreduce_bytes": nbytes,
+           "allreduce_bus_GBs": round(2.0 * (world - 1) / world * nbytes / 1e9 / (seg[1] / 1e3), 1) if world > 1 else None,
+           "allreduce_share_of_step": round(seg[1] / seg[3], 4),
+           "MP_s_all_ranks": round(world * B3 * cfg.test_steps * H * W / 1e6 / (seg[3] / 1e3), 1),
+           "note": "gradients of Agent + Value live in one flat buffer (dist.GradBucket): the all-reduce is a single "
+                   "NCCL call on memory the captured backward accumulated into, issued right after the graph; "
+                   "times are max over ranks"}
+    return res
 
 
 # ----------------------------------------------------------------------------------------------
@@ -398,6 +533,82 @@ def run_b200(args):
     h2d = host_img.numel() * 4 + host_feat.numel() * 4
     d2h = host_out.numel() * 4
 
+    # ---------------- the PCIe bound of that loop, measured with every rank copying at once ----------------
+    pcie = pcie_probe(dev, world, barrier, dist, host_img.numel() * 4)
+
+    # ---------------- e2e, second mode: the image pool resident in HBM (DeviceReplayPool) ----------------
+    # train.py:245-255,378-381 keep the pool of partially retouched frames on the HOST: every iteration
+    # uploads a batch and downloads the retouched one.  With the pool in HBM only FRESH frames cross PCIe
+    # (a trajectory lasts cfg.test_steps = 5 steps, so ~1/5 of a batch per step), on a side stream, and the
+    # per-step download is the step's metric, not the pixels.
+    import random as _random
+    from adaptiveisp_b200.pipeline import GraphedStep
+    from adaptiveisp_b200.replay_pool import DeviceReplayPool
+    n_store = 128
+    frame_store = torch.empty((n_store, 3, H, W), dtype=torch.float32, pin_memory=True)
+    for k in range(0, n_store, B):
+        frame_store[k:k + B].copy_(host_img[:min(B, n_store - k)])
+    cursor = {"i": 0}
+
+    def fetch(n):
+        i = cursor["i"]
+        idx = [(i + k) % n_store for k in range(n)]
+        cursor["i"] = (i + n) % n_store
+        lo = idx[0]
+        imgs = frame_store[lo:lo + n] if lo + n <= n_store else torch.cat([frame_store[lo:], frame_store[:(lo + n) % n_store]])
+        return imgs, [None] * n
+
+    pool = DeviceReplayPool(cfg, (3, H, W), dev, fetch, capacity=128, fetch_batch=16, rng=_random.Random(5 + rank))
+    feats_dev = (feats * 0.05).contiguous()
+
+    def pool_step(x, ft):
+        out = isp_step(x, ft).detach()
+        return out, out.mean(dim=(1, 2, 3))
+
+    for f in flts:
+        f.zero_grad(set_to_none=True)
+    gpool = GraphedStep(pool_step, (img, feats_dev), modules=flts)
+    host_metric = torch.empty((B,), dtype=torch.float32, pin_memory=True)
+    t_steps = float(cfg.test_steps)
+
+    def pool_run(nsteps):
+        for _ in range(nsteps):
+            batch = pool.get_batch(B)
+            out, metric = gpool(batch.images, feats_dev)
+            ns = batch.states.clone()
+            ns[:, 2] += 1.0
+            ns[:, 1] = (ns[:, 2] >= t_steps).to(ns.dtype)
+            host_rows = [[0.0, 1.0 if pool._steps[sl] + 1 >= t_steps else 0.0, pool._steps[sl] + 1] for sl in batch.slots]
+            pool.put_back(batch.slots, out, ns, states_host=host_rows)
+            host_metric.copy_(metric, non_blocking=True)
+
+    pool_run(6)                                   # reach the steady mix of trajectory ages
+    pool_vals = []
+    h2d_before = pool.h2d_bytes
+    for _rep in range(3):
+        barrier()
+        tw2 = time.time()
+        e0.record()
+        pool_run(e2e_steps)
+        e1.record()
+        barrier()
+        tw3 = time.time()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pool_vals.append(world * px_step * e2e_steps / 1e6 / (float(t.item()) / 1e3))
+        win.append((tw2, tw3))
+    pool_h2d_per_step = (pool.h2d_bytes - h2d_before) / (3 * e2e_steps)
+    del pool, gpool, frame_store
+
+    # ---------------- N > 1: the rollout + gradient all-reduce of BASELINE configs[2] ----------------
+    allreduce = None
+    if world > 1 and not args.no_extras:
+        try:
+            allreduce = rollout_allreduce_section(dev, world, barrier, dist)
+        except Exception as e:                  # never invalidates the headline line
+            allreduce = {"error": repr(e)[:300]}
+
     if rank == 0:
         peak, peak_src = peaks()
         npx = B * H * W
@@ -421,11 +632,8 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "height": H, "width": W, "filters": names,
-                       "l2": "per step and GPU: 201 MB image, 2.0 GB of upstream gradients (one per filter) read, 2.0 GB "
-                             "output stack written -- far beyond the 126 MB L2; no flush",
-                       "parallelism": f"dp{world} (batch-sharded replicas, no collective in the ISP path)"},
-            "roofline": {"bound": "hbm", "kernel": ("nlm_kernel<grad>" if dom["filter"] == "NLM" else dom["filter"]) +
+            "config": bench_config(world),
+            "roofline": {"bound": "sm_issue" if dom["filter"] == "NLM" else "hbm", "kernel": ("nlm_kernel<grad>" if dom["filter"] == "NLM" else dom["filter"]) +
                          (" fwd" if dom_fwd else " bwd"), "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "peak_source": peak_src,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
@@ -453,6 +661,18 @@ def run_b200(args):
             "kernels": klist,
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "windows": e2e_windows, "pinned_numa_node": numa_node,
+                    # the loop moves h2d + d2h bytes per step through PCIe in both directions at once: its
+                    # bound is the measured duplex rate (every rank copying concurrently, slowest rank)
+                    "pcie": pcie,
+                    "pcie_bound_MP_s": world * px_step / 1e6 / (max(h2d, d2h) / 1e9 / pcie["duplex_per_dir_GBs_min_rank"]),
+                    "pcie_frac": (max(h2d, d2h) / 1e9 / (world * px_step / 1e6 / e2e_value)) / pcie["duplex_per_dir_GBs_min_rank"],
+                    "pool_resident": {
+                        "value": sorted(pool_vals)[1], "unit": "MP/s", "windows": [round(v, 1) for v in pool_vals],
+                        "h2d_bytes_per_step": pool_h2d_per_step, "d2h_bytes_per_step": B * 4,
+                        "api": "DeviceReplayPool (train.py's image pool kept in HBM: draw a batch, one graphed 10-filter "
+                               "step fwd+bwd, put the retouched batch back; only fresh frames are uploaded, on a side "
+                               "stream, and the per-step download is the step's metric) -- reported beside the "
+                               "copy-every-step figure above, which stays the headline"},
                     "api": "FilterBank over the 10 drop-in Filter modules (their FC layers + regressors, one banked "
                            "kernel set) + .backward(), replayed as one CUDA graph per step by GraphedHostLoop with "
                            "double-buffered pinned-host copies",
@@ -460,6 +680,8 @@ def run_b200(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks.summary([(tw0, tw1)] + win),
         }
+        if allreduce is not None:
+            line["rollout_allreduce"] = allreduce
         if world == 1 and not args.no_extras:
             try:
                 line["extras"] = extras(dev, L, peak)

@@ -205,6 +205,29 @@ int aisp_select_apply_bwd(const float* img, const float* out, const float* grad_
                           void* scratch, size_t scratch_bytes, void* stream);
 
 /*
+ * Sequence launch set: the general forward of the path.  Every sample b runs its own op sequence
+ * ops[b, 0..seq_len[b]) that may hold per-pixel steps and AT MOST ONE stencil step (SHARPEN, SHARPEN_V2,
+ * USM or NLM) anywhere in it -- the fixed chain of isp/filters.py:753-815 (E -> G -> WB -> CCM -> Shr),
+ * the policy-selected single step of agent.py:103-154 (S == 1) and the replayed pipelines of
+ * yolov3/val_adaptiveisp.py:291-327.  Three kernels are issued back to back (per-pixel, sharpen family,
+ * NLM); each sample is processed by exactly one of them, per-pixel steps before the stencil step run on
+ * the staged tile, steps after it on the outputs in registers: 24 B/px for the whole sequence.  A second
+ * stencil step ends the sequence there (a host-side planner splits such pipelines into several calls).
+ *   hr_img / hr_out  [B,3,hr_H,hr_W] or NULL: the high-resolution twin of the batch gets the SAME
+ *                    sequences and parameters (isp/filters.py:116-122, agent.py:155-157, train.py:541) as
+ *                    extra tiles of the same per-pixel / sharpen launches (NLM: a second launch)
+ *   down             [B,3,down_h,down_w] or NULL: block means of `out` (== nn.AdaptiveAvgPool2d for evenly
+ *                    dividing sizes: what agent.py:97 and value.py:63 compute next from the retouched
+ *                    image), emitted from the kernels' store path where the pooling blocks tile the CTA's
+ *                    work (512x512 -> 64x64 does) and completed by one masked pass for the rest (NLM samples)
+ *   nlm_dout_dh / nlm_wsum   training stashes of the NLM samples (see aisp_nlm_fwd); S == 1 only
+ * clip_each: AISP_SEQ_CLIP or 0.
+ */
+int aisp_sequence_fwd(const float* img, float* out, const float* params, const int32_t* ops, const int32_t* seq_len,
+                      int B, int H, int W, int S, int clip_each, const float* hr_img, float* hr_out, int hr_H, int hr_W,
+                      float* down, int down_h, int down_w, float* nlm_dout_dh, float* nlm_wsum, void* stream);
+
+/*
  * Device-side filter selection + agent-state update in one launch, no host round trip:
  * pdf_sample / argmax / forced id (agent.py:12-16,126-149), one_hot (agent.py:18-23), the gather
  * of the selected filter's parameter row (the B200 form of agent.py:154: pick the row before the

@@ -44,7 +44,7 @@ int main(void) {
     CK(cudaMemset(d_scr, 0, scr));
     CK(cudaMemcpy(d_img, h_img, sizeof(float) * n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_g, h_g, sizeof(float) * n, cudaMemcpyHostToDevice));
-    if (aisp_version() != 2 || aisp_op_num_params(AISP_OP_CCM) != 9) return fail("version/params", aisp_version(), 2);
+    if (aisp_version() != 3 || aisp_op_num_params(AISP_OP_CCM) != 9) return fail("version/params", aisp_version(), 3);
 
     /* 1. fused sequence: exposure +1 EV -> white balance (0.5,0.5,0.5) -> exposure 0 == identity */
     const int S = 3;

@@ -47,6 +47,18 @@ def _worker(rank, world, port, out):
     ok = ok and all(p.grad is None for p in unused.parameters())
     ok = ok and all(float(p.grad.abs().max()) == 0.0 for p in zero.parameters())
     ok = ok and nbytes == 4 * sum(p.numel() for p in list(net.parameters()) + list(zero.parameters()))
+    # the grads now live in ONE persistent flat buffer: a second backward accumulates into it in place and
+    # the next all-reduce needs no gather / scatter copies
+    bucket = params[0]._aisp_grad_bucket
+    ok = ok and bucket.attached() and bucket.nbytes == nbytes
+    ptrs = [p.grad.data_ptr() for p in bucket.params]
+    bucket.zero()
+    net(x_all[lo:hi]).sum().backward()
+    ok = ok and [p.grad.data_ptr() for p in bucket.params] == ptrs
+    ok = ok and allreduce_grads(params, average=False) == nbytes and params[0]._aisp_grad_bucket is bucket
+    ok = ok and all(torch.allclose(a.grad, b.grad, atol=1e-5) for a, b in zip(net.parameters(), ref.parameters()))
+    total = bucket.clip_grad_norm_(1e-5)
+    ok = ok and float(total) > 0 and float(torch.linalg.vector_norm(bucket.flat)) <= 1.001e-5
     out[rank] = bool(ok)
     dist.destroy_process_group()
 

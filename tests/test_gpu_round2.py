@@ -39,6 +39,14 @@ def cfg():
     return make_cfg()
 
 
+def grad64(op, img, p, g, clip=True):
+    """The reference formula of one filter evaluated in fp64 (oracle on double tensors) -> d/d param."""
+    p64 = p.double().clone().requires_grad_(True)
+    y = (O.forward if clip else O.run)(op, img.double(), p64)
+    (y * g.double()).sum().backward()
+    return p64.grad.reshape(-1).numpy()
+
+
 def elem_err(a, b, floor=GRAD_FLOOR):
     """Worst per-element relative error |a-b| / max(|b|, floor * max|b|) and where it occurs."""
     a = np.asarray(a, np.float64).reshape(-1)
@@ -66,11 +74,25 @@ class Checks:
         if not e <= tol:
             self.bad.append(f"{tag}: output err {e:.3g} > {tol}")
 
-    def grad(self, a, b, tol, tag):
+    def grad(self, a, b, tol, tag, ref64=None):
+        """Per-element bound against the reference's fp32 autograd; where that fails and an fp64 evaluation
+        of the same formula is supplied (`ref64`, a callable, evaluated lazily), the CUDA value must be at
+        least as close to it as the reference's own fp32 value is (its summation noise is then the cause)."""
         e, i = elem_err(a, b)
-        if not e <= tol:
-            self.bad.append(f"{tag}: component {i} got {np.asarray(a).reshape(-1)[i]:.8g} want "
-                            f"{np.asarray(b).reshape(-1)[i]:.8g} (per-element rel err {e:.3g} > {tol})")
+        if e <= tol:
+            return
+        msg = (f"{tag}: component {i} got {np.asarray(a).reshape(-1)[i]:.8g} want "
+               f"{np.asarray(b).reshape(-1)[i]:.8g} (per-element rel err {e:.3g} > {tol})")
+        if ref64 is not None:
+            r64 = np.asarray(ref64(), np.float64).reshape(-1)
+            a64, b64 = np.asarray(a, np.float64).reshape(-1), np.asarray(b, np.float64).reshape(-1)
+            den = np.maximum(np.abs(r64), GRAD_FLOOR * np.abs(r64).max())
+            e_cuda, e_ref = np.abs(a64 - r64) / den, np.abs(b64 - r64) / den
+            if np.all(e_cuda <= np.maximum(tol, 1.5 * e_ref)):
+                return
+            j = int(np.argmax(e_cuda - np.maximum(tol, 1.5 * e_ref)))
+            msg += f"; vs fp64: cuda err {e_cuda[j]:.3g}, reference-fp32 err {e_ref[j]:.3g} at component {j}"
+        self.bad.append(msg)
 
     def norm(self, a, b, tol, tag):
         e = rel_err(a, b)
@@ -112,7 +134,9 @@ def test_config2_full_size_bank_vs_oracle(dev):
             tag = f"image {b} {O.OP_NAMES[op]}"
             chk.out(y[b:b + 1, f].detach().cpu().numpy(), yc.detach().numpy(), OUT_ATOL, tag)
             n = O.OP_NPARAMS[op]
-            chk.grad(Pd.grad[b, f, :n].cpu().numpy(), pc.grad.reshape(-1).numpy(), GRAD_RTOL, tag)
+            chk.grad(Pd.grad[b, f, :n].cpu().numpy(), pc.grad.reshape(-1).numpy(), GRAD_RTOL, tag,
+                     ref64=(None if op == O.OP_NLM else
+                            (lambda op=op, b=b, f=f: grad64(op, img[b:b + 1], plist[f][b:b + 1], g[b:b + 1, f].cpu()))))
             checked += 1
     chk.done()
     assert checked == 19
@@ -152,7 +176,9 @@ def test_config2_full_size_agent_select_vs_oracle(dev):
         tag = f"sample {b} {O.OP_NAMES[op]}"
         chk.out(y[b:b + 1].detach().cpu().numpy(), yc.detach().numpy(), OUT_ATOL, tag)
         n = O.OP_NPARAMS[op]
-        chk.grad(Pd.grad[b, :n].cpu().numpy(), pc.grad.reshape(-1).numpy(), GRAD_RTOL, tag)
+        chk.grad(Pd.grad[b, :n].cpu().numpy(), pc.grad.reshape(-1).numpy(), GRAD_RTOL, tag,
+                 ref64=(None if op == O.OP_NLM else
+                        (lambda op=op, b=b: grad64(op, img[b:b + 1], plist[b], g[b:b + 1].cpu()))))
     chk.done()
     assert len(seen) == 10
 
@@ -252,26 +278,38 @@ def test_tone_v2_flat_params_run_v2_predict_param(F, cfg, dev):
 def test_nonfinite_inputs_propagate_like_the_reference(F, cfg, dev, op, clip):
     """NaN and +-inf planted in single channels: the set of non-finite output values must be the
     reference's, element for element (torch.clamp / maximum / max(dim) keep NaN, and the wrapper's
-    lerp `0 * img + process` turns an inf pixel into NaN), and every finite value must still match."""
+    lerp `0 * img + process` turns an inf pixel into NaN), and every finite value must still match.
+    The stencil filters go through a library convolution in the reference (oneDNN on the CPU, cuDNN on a
+    GPU), whose treatment of inf inside a window is the library's own; there only NaN is planted for the
+    exact comparison and inf is checked as "the batch is flagged non-finite on both sides"."""
     B, H, W = 2, 12, 16
     img = cases.edge_image(B, H, W, seed=13, in_range=True)
     nan, inf = float("nan"), float("inf")
+    stencil = op in cases.STENCIL_OPS
     img[0, 0, 3, 3] = nan
     img[0, 1, 3, 6] = nan
     img[0, 2, 5, 9] = nan
-    img[1, 0, 4, 4] = inf
-    img[1, 1, 6, 7] = -inf
-    img[1, 2, 8, 2] = inf
     img[1, :, 9, 9] = nan
+    if not stencil:
+        img[1, 0, 4, 4] = inf
+        img[1, 1, 6, 7] = -inf
+        img[1, 2, 8, 2] = inf
     _, p = cases.params_for(op, B, seed=13)
     ref = (O.forward if clip else O.run)(op, img, p)
     flt = cls_for(F, op)(cfg).to(dev)
-    got = (flt(img.to(dev), specified_parameter=p.to(dev))[0] if clip else flt.run(img.to(dev), p.to(dev))).cpu()
+    run = (lambda x: flt(x.to(dev), specified_parameter=p.to(dev))[0].cpu()) if clip else (lambda x: flt.run(x.to(dev), p.to(dev)).cpu())
+    got = run(img)
     assert torch.equal(torch.isnan(got), torch.isnan(ref)), O.OP_NAMES[op]
     assert torch.equal(torch.isposinf(got), torch.isposinf(ref)) and torch.equal(torch.isneginf(got), torch.isneginf(ref))
     fin = torch.isfinite(ref)
     assert out_err(got[fin].numpy(), ref[fin].numpy()) <= OUT_ATOL, O.OP_NAMES[op]
     assert int(torch.isnan(ref).sum()) >= 4      # the case really exercises the propagation
+    if stencil:
+        img2 = cases.edge_image(B, H, W, seed=14, in_range=True)
+        img2[1, 2, 6, 5] = inf
+        ref2, got2 = (O.forward if clip else O.run)(op, img2, p), run(img2)
+        assert not bool(torch.isfinite(ref2).all()) and not bool(torch.isfinite(got2).all())
+        assert bool(torch.isfinite(got2[0]).all()) and bool(torch.isfinite(ref2[0]).all())
 
 
 def test_nan_batch_trips_the_pool_refill_guard(F, cfg, dev):
@@ -446,3 +484,174 @@ def test_fused_chain_identity_none_and_strictness(dev):
                        torch.zeros((B, 7), dtype=torch.int32, device=dev))
     y7 = AF.apply_chain(x.detach(), torch.zeros((B, 7, 24), device=dev), torch.zeros((B, 7), dtype=torch.int32, device=dev))
     assert y7.shape == x.shape                                                           # forward-only: up to 8 steps
+
+
+# ----------------------------------------------------------------------------------------------
+# 7. sequence launch set (aisp_sequence_fwd): one stencil step anywhere in a sequence, one pass over HBM
+# ----------------------------------------------------------------------------------------------
+def _seq_case(seqs, H, W, seed):
+    B = len(seqs)
+    S = max(len(s) for s in seqs)
+    img = cases.edge_image(B, H, W, seed=seed, in_range=True)
+    ops = torch.zeros((B, S), dtype=torch.int32)
+    lens = torch.tensor([len(s) for s in seqs], dtype=torch.int32)
+    P = torch.zeros((B, S, 24))
+    plist = []
+    for b, seq in enumerate(seqs):
+        row = []
+        for k, op in enumerate(seq):
+            _, p = cases.params_for(op, 1, seed=seed + 13 * b + k)
+            if op == O.OP_NLM:
+                p = torch.tensor([[0.15 + 0.1 * b]])
+            row.append(p)
+            ops[b, k] = op
+            P[b, k, :O.OP_NPARAMS[op]] = p.reshape(-1)
+        plist.append(row)
+    return img, ops, lens, P, plist
+
+
+SEQS = [
+    [O.OP_EXPOSURE, O.OP_GAMMA, O.OP_WB, O.OP_CCM, O.OP_SHARPEN],      # isp/filters.py:753-815 in ONE launch
+    [O.OP_EXPOSURE, O.OP_GAMMA, O.OP_WB, O.OP_CCM, O.OP_USM],          # ... and its USM variant
+    [O.OP_WNB, O.OP_NLM, O.OP_TONE],                                   # prologue + NLM + epilogue
+    [O.OP_SHARPEN_V2, O.OP_CONTRAST, O.OP_SATPLUS],                    # stencil first
+    [O.OP_TONE, O.OP_CCM],                                             # no stencil at all
+    [O.OP_NLM],                                                        # a lone stencil
+    [O.OP_GAMMA, O.OP_COLOR, O.OP_USM, O.OP_EXPOSURE, O.OP_WNB, O.OP_TONE, O.OP_CCM, O.OP_WB],   # 8 steps
+    [],                                                                # idle sample: carried through
+]
+
+
+@pytest.mark.parametrize("clip_each", [True, False])
+@pytest.mark.parametrize("size", [(40, 56), (33, 47), (48, 264)])
+def test_sequence_launch_set_matches_oracle(dev, clip_each, size):
+    """Heterogeneous per-sample sequences, each with at most one stencil step somewhere in it, run by ONE
+    launch set; (33,47): scalar / cp.async paths; (48,264): W % 4 == 0 and W > 256 -> TMA tiles, interior
+    and frame, a USM tile whose halo leaves the image."""
+    from adaptiveisp_b200 import functional as AF
+    H, W = size
+    img, ops, lens, P, plist = _seq_case(SEQS, H, W, seed=5 + H)
+    got, _, _ = AF.sequence_forward(img.to(dev), P.to(dev), ops.to(dev), lens.to(dev), clip_each=clip_each)
+    got = got.cpu()
+    chk = Checks()
+    for b, seq in enumerate(SEQS):
+        ref = O.chain(seq, img[b:b + 1], plist[b], clip_each) if seq else img[b:b + 1]
+        chk.out(got[b:b + 1].numpy(), ref.numpy(), 1e-5 * max(len(seq), 3), f"sample {b} {[O.OP_NAMES[o] for o in seq]}")
+    chk.done()
+
+
+def test_sequence_second_stencil_ends_the_sequence_and_planner_splits(dev):
+    """Two stencil steps cannot share one pass (the second needs the first's output at neighbouring
+    pixels): the kernel stops a sequence in front of the second one, and replay.plan_pipeline splits such
+    pipelines into phases -- BASELINE configs[3]'s BW -> NLM -> USM becomes [BW -> NLM], [USM]."""
+    from adaptiveisp_b200 import functional as AF, replay
+    seqs = [[O.OP_WNB, O.OP_NLM, O.OP_USM, O.OP_GAMMA], [O.OP_SHARPEN, O.OP_SHARPEN]]
+    img, ops, lens, P, plist = _seq_case(seqs, 36, 44, seed=9)
+    got, _, _ = AF.sequence_forward(img.to(dev), P.to(dev), ops.to(dev), lens.to(dev))
+    assert out_err(got[0:1].cpu().numpy(), O.chain(seqs[0][:2], img[0:1], plist[0][:2], True).numpy()) <= 3e-5
+    assert out_err(got[1:2].cpu().numpy(), O.chain(seqs[1][:1], img[1:2], plist[1][:1], True).numpy()) <= OUT_ATOL
+    plan = replay.plan_pipeline(seqs, plist, dev)
+    assert len(plan.phases) == 2
+    full = replay.execute_plan(img.to(dev), plan).cpu()
+    for b in range(2):
+        assert out_err(full[b:b + 1].numpy(), O.chain(seqs[b], img[b:b + 1], plist[b], True).numpy()) <= 4e-5, b
+
+
+def test_high_res_twin_in_the_same_launch_set(dev):
+    """isp/filters.py:116-122 / agent.py:155-157 / train.py:541: the sequences and parameters of the
+    low-resolution batch applied to a full-size twin (odd, unaligned shape: its own scalar launch; aligned
+    shape: extra tiles of the same launch)."""
+    from adaptiveisp_b200 import functional as AF
+    seqs = [[O.OP_GAMMA], [O.OP_SHARPEN], [O.OP_NLM], [O.OP_EXPOSURE, O.OP_USM, O.OP_TONE], [O.OP_SATPLUS, O.OP_CCM]]
+    img, ops, lens, P, plist = _seq_case(seqs, 64, 64, seed=21)
+    for (H2, W2) in [(75, 131), (96, 160)]:
+        hi = cases.lod_batch(len(seqs), H2, W2, seed=22, letterbox=False)
+        lo_out, hi_out, _ = AF.sequence_forward(img.to(dev), P.to(dev), ops.to(dev), lens.to(dev), high_res=hi.to(dev))
+        chk = Checks()
+        for b, seq in enumerate(seqs):
+            chk.out(lo_out[b:b + 1].cpu().numpy(), O.chain(seq, img[b:b + 1], plist[b], True).numpy(), 3e-5, f"low {b}")
+            chk.out(hi_out[b:b + 1].cpu().numpy(), O.chain(seq, hi[b:b + 1], plist[b], True).numpy(), 3e-5, f"high {b} {H2}x{W2}")
+        chk.done()
+
+
+@pytest.mark.parametrize("size,out", [((512, 512), (64, 64)), ((256, 256), (64, 64)), ((96, 160), (32, 32)),
+                                      ((64, 64), (64, 64)), ((128, 512), (16, 64))])
+def test_block_means_leave_through_the_store_path(dev, size, out):
+    """the pooled image that agent.py:97 / value.py:63 compute next comes out of the apply
+    itself -- from the per-pixel and sharpen kernels' store path where pooling blocks tile a CTA's work
+    (512 -> 64, 256 -> 64), from one masked block-mean pass otherwise (NLM samples, 3x5 blocks)."""
+    from adaptiveisp_b200 import functional as AF
+    H, W = size
+    ops = [O.OP_GAMMA, O.OP_SHARPEN, O.OP_NLM, -1, O.OP_USM, O.OP_CCM, O.OP_SATPLUS]
+    B = len(ops)
+    img = cases.lod_batch(B, H, W, seed=31)
+    rows = []
+    for b, op in enumerate(ops):
+        if op < 0:
+            rows.append(torch.zeros((1, 24)))
+        else:
+            rows.append(AF.pack_params(cases.params_for(op, 1, seed=40 + b)[1], O.OP_NPARAMS[op]))
+    P = torch.cat(rows, 0).to(dev)
+    ops_t = torch.tensor(ops, dtype=torch.int32, device=dev)
+    y, _, down = AF.apply_ops(img.to(dev), P, ops_t, clip=True, down_hw=out)
+    y_plain = AF.apply_ops(img.to(dev), P, ops_t, clip=True)
+    assert torch.equal(y, y_plain)                                   # the emitting kernels compute the same image
+    ref = torch.nn.AdaptiveAvgPool2d(out)(y.double()).float()
+    assert down.shape == ref.shape
+    err = (down - ref).abs().amax(dim=(1, 2, 3)).cpu().tolist()
+    assert max(err) <= 3e-7, err
+    assert float(down[3].abs().max()) == 0.0                         # AISP_OP_NONE: zero image, zero means
+
+
+def test_gradient_through_emitted_block_means(dev):
+    """train.py:283: the critic pools the RETOUCHED image (value.py:63), so a gradient reaches the block
+    means; it must act on the filter parameters exactly as if the image had been pooled by PyTorch."""
+    from adaptiveisp_b200 import functional as AF
+    ops = [O.OP_EXPOSURE, O.OP_TONE, O.OP_SHARPEN, O.OP_NLM, O.OP_CCM]
+    B, H, W = len(ops), 128, 128
+    img = cases.lod_batch(B, H, W, seed=51, device=dev)
+    P0 = torch.cat([AF.pack_params(cases.params_for(op, 1, seed=60 + b)[1], O.OP_NPARAMS[op]) for b, op in enumerate(ops)], 0)
+    ops_t = torch.tensor(ops, dtype=torch.int32, device=dev)
+    g = cases.grad_out((B, 3, H, W), 5).to(dev)
+    gd = cases.grad_out((B, 3, 16, 16), 6).to(dev).abs()
+    Pa = P0.to(dev).requires_grad_(True)
+    y, _, down = AF.apply_ops(img, Pa, ops_t, clip=True, down_hw=(16, 16))
+    ((y * g).sum() + (down * gd).sum()).backward()
+    Pb = P0.to(dev).requires_grad_(True)
+    y2 = AF.apply_ops(img, Pb, ops_t, clip=True)
+    ((y2 * g).sum() + (torch.nn.AdaptiveAvgPool2d((16, 16))(y2) * gd).sum()).backward()
+    for b, op in enumerate(ops):
+        n = O.OP_NPARAMS[op]
+        assert_grad(Pa.grad[b, :n].cpu().numpy(), Pb.grad[b, :n].cpu().numpy(), 2e-5, O.OP_NAMES[op])
+    # only the pooled image is used: the full-resolution gradient is absent altogether
+    Pc = P0.to(dev).requires_grad_(True)
+    _, _, d3 = AF.apply_ops(img, Pc, ops_t, clip=True, down_hw=(16, 16))
+    (d3 * gd).sum().backward()
+    assert bool(torch.isfinite(Pc.grad).all()) and float(Pc.grad.abs().max()) > 0
+
+
+def test_agent_output_carries_block_means_for_the_critic(dev):
+    """Agent.forward attaches the emitted block means to the retouched image; the next Agent step and the
+    drop-in critic use them instead of pooling the full-resolution image again."""
+    from adaptiveisp_b200.agent import Agent
+    from adaptiveisp_b200.config import make_cfg
+    from adaptiveisp_b200.value import Value
+    torch.manual_seed(11)
+    cfg = make_cfg(feature_extractor_dims=64, base_channels=4, fc1_size=16, dropout_keep_prob=1.0)
+    agent = Agent(cfg, shape=(16, 64, 64), device=dev).to(dev).eval()
+    value = Value(cfg, shape=(19, 64, 64)).to(dev).eval()
+    B = 6
+    x = cases.lod_batch(B, 512, 512, seed=71, device=dev)
+    z = torch.rand((B, cfg.z_dim), device=dev)
+    s0 = torch.zeros((B, cfg.num_state_dim), device=dev)
+    with torch.no_grad():
+        (y, s1, _sur, _pen), dbg, _ = agent((x, z, s0), 1.0)
+        ref_down = torch.nn.AdaptiveAvgPool2d((64, 64))(y.double()).float()
+        assert float((y._aisp_down - ref_down).abs().max()) <= 3e-7
+        assert agent.downsample(y) is y._aisp_down
+        v_fast = value(y, s1)
+        v_ref = value(y.clone(), s1)                 # a plain tensor: pooled by the block-mean kernel
+        assert float((v_fast - v_ref).abs().max()) <= 1e-5
+        (y2, s2, _, _), _, _ = agent((y, z, s1), 1.0)   # second step consumes the emitted means
+        (y2r, s2r, _, _), _, _ = agent((y.clone(), z, s1), 1.0)
+        assert torch.equal(s2, s2r) and float((y2 - y2r).abs().max()) <= 1e-5

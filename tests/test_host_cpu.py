@@ -32,7 +32,7 @@ def header_symbols():
 def test_library_exports_every_declared_symbol(lib):
     from adaptiveisp_b200 import _lib
     syms = header_symbols()
-    assert len(syms) == 19
+    assert len(syms) == 20
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/aisp_b200.h but not exported"
     assert set(syms) == set(_lib.SIGNATURES), "ctypes binding and header disagree"
@@ -210,7 +210,9 @@ def test_replay_segmentation_and_reference_file_formats():
     from adaptiveisp_b200.config import make_cfg
     E, G, CCM, SHR, NLM, T = O.OP_EXPOSURE, O.OP_GAMMA, O.OP_CCM, O.OP_SHARPEN, O.OP_NLM, O.OP_TONE
     assert replay.segment([E, G, CCM]) == [[0, 1, 2]]
-    assert replay.segment([E, SHR, G, T, NLM]) == [[0], [1], [2, 3], [4]]
+    # a segment = per-pixel steps around AT MOST ONE stencil step (one aisp_sequence_fwd pass over HBM)
+    assert replay.segment([E, SHR, G, T, NLM]) == [[0, 1, 2, 3], [4]]
+    assert replay.segment([E, G, SHR]) == [[0, 1, 2]]                       # isp/filters.py:753-815 style chain
     assert replay.segment([NLM, NLM]) == [[0], [1]]
     assert replay.segment([]) == []
     assert [len(s) for s in replay.segment([E] * 11)] == [8, 3]            # AISP_MAX_STEPS per fused pass
@@ -243,3 +245,51 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["value"] == d["value"] and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_value_dropin_matches_reference_on_cpu():
+    """The critic stays PyTorch; the drop-in must load the reference's state_dict strictly and, on CPU
+    tensors (no kernels involved), reproduce its output bit for bit -- pooled image, luminance /
+    contrast / saturation statistics (value.py:63-75) and the nets."""
+    if not ref_shim.available():
+        pytest.skip("reference checkout not present")
+    from adaptiveisp_b200.config import make_cfg
+    from adaptiveisp_b200.value import Value, value_statistics
+    ref = ref_shim.load()
+    cfg = make_cfg(feature_extractor_dims=64, base_channels=4, fc1_size=16)
+    torch.manual_seed(0)
+    theirs = ref.value.Value(cfg, shape=(19, 64, 64)).eval()
+    ours = Value(cfg, shape=(19, 64, 64)).eval()
+    ours.load_state_dict(theirs.state_dict(), strict=True)
+    x = cases.lod_batch(3, 128, 192, seed=3)
+    states = torch.rand((3, cfg.num_state_dim))
+    with torch.no_grad():
+        assert torch.equal(ours(x, states), theirs(x, states))
+    # an image that carries emitted block means uses them instead of pooling again
+    x2 = x.clone()
+    x2._aisp_down = torch.nn.AdaptiveAvgPool2d((64, 64))(x)
+    with torch.no_grad():
+        assert torch.equal(ours(x2, states), theirs(x, states))
+    st = value_statistics(torch.nn.AdaptiveAvgPool2d((64, 64))(x))
+    assert st.shape == (3, 3) and bool((st[:, 1] >= 0).all())
+
+
+def test_replay_pool_reports_exhaustion_instead_of_spinning():
+    """get_batch with every record checked out (no put_back / discard in between) must raise, not loop."""
+    import random
+    from adaptiveisp_b200.config import make_cfg
+    from adaptiveisp_b200.replay_pool import DeviceReplayPool
+    cfg = make_cfg(replay_memory_size=6)
+    n = {"k": 0}
+
+    def fetch(k):
+        n["k"] += k
+        return torch.zeros((k, 3, 4, 4)), [{"id": i} for i in range(k)]
+
+    pool = DeviceReplayPool(cfg, (3, 4, 4), "cpu", fetch, fetch_batch=3, rng=random.Random(0))
+    a = pool.get_batch(4)
+    with pytest.raises(RuntimeError, match="exhausted"):
+        pool.get_batch(4)                       # only 2 records left and nothing to refill
+    assert len(pool) == 2                       # the failed draw put its picks back
+    pool.put_back(a.slots, a.images, a.states)
+    assert len(pool.get_batch(4).slots) == 4
