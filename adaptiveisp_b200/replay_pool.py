@@ -65,6 +65,15 @@ class DeviceReplayPool:
         self.fill()
 
     # ------------------------------------------------------------------------------------------
+    def _index(self, values: Sequence[int]) -> torch.Tensor:
+        """Slot / row indices as a device tensor WITHOUT a blocking copy: torch.tensor(list, device=cuda)
+        goes through pageable memory and stalls the host until the stream drains, which would serialise
+        every training iteration; a pinned staging copy keeps the enqueue asynchronous."""
+        t = torch.tensor(list(values), dtype=torch.long)
+        if self.device.type != "cuda":
+            return t
+        return t.pin_memory().to(self.device, non_blocking=True)
+
     def __len__(self) -> int:
         return len(self._live)
 
@@ -76,7 +85,7 @@ class DeviceReplayPool:
             if imgs.shape[0] != n or len(metas) != n:
                 raise ValueError("fetch_fresh(n) must return n images and n meta records")
             slots = [self._free.pop() for _ in range(n)]
-            idx = torch.tensor(slots, dtype=torch.long, device=self.device)
+            idx = self._index(slots)
             if self._h2d is not None:
                 with torch.cuda.stream(self._h2d):
                     src = imgs.to(self.device, dtype=torch.float32, non_blocking=True)
@@ -119,7 +128,7 @@ class DeviceReplayPool:
                     chosen.append(s)         # finished images are dropped, as in the reference
                 else:
                     self._release(s)
-        idx = torch.tensor(chosen, dtype=torch.long, device=self.device)
+        idx = self._index(chosen)
         return PoolBatch(images=self.images.index_select(0, idx), states=self.states.index_select(0, idx),
                          slots=chosen, meta=[self.meta[s] for s in chosen])
 
@@ -145,8 +154,8 @@ class DeviceReplayPool:
             else:
                 self._release(s)
         if keep_rows:
-            rows = torch.tensor(keep_rows, dtype=torch.long, device=self.device)
-            idx = torch.tensor(keep_slots, dtype=torch.long, device=self.device)
+            rows = self._index(keep_rows)
+            idx = self._index(keep_slots)
             self.images.index_copy_(0, idx, images.detach().index_select(0, rows))
             self.states.index_copy_(0, idx, states.detach().index_select(0, rows).to(torch.float32))
             self._live.extend(keep_slots)

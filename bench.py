@@ -550,13 +550,10 @@ def run_b200(args):
         frame_store[k:k + B].copy_(host_img[:min(B, n_store - k)])
     cursor = {"i": 0}
 
-    def fetch(n):
-        i = cursor["i"]
-        idx = [(i + k) % n_store for k in range(n)]
-        cursor["i"] = (i + n) % n_store
-        lo = idx[0]
-        imgs = frame_store[lo:lo + n] if lo + n <= n_store else torch.cat([frame_store[lo:], frame_store[:(lo + n) % n_store]])
-        return imgs, [None] * n
+    def fetch(n):                                  # a contiguous (hence still pinned) slice of the host frame store
+        lo = cursor["i"] if cursor["i"] + n <= n_store else 0
+        cursor["i"] = (lo + n) % n_store
+        return frame_store[lo:lo + n], [None] * n
 
     pool = DeviceReplayPool(cfg, (3, H, W), dev, fetch, capacity=128, fetch_batch=16, rng=_random.Random(5 + rank))
     feats_dev = (feats * 0.05).contiguous()

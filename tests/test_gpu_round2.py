@@ -655,3 +655,52 @@ def test_agent_output_carries_block_means_for_the_critic(dev):
         (y2, s2, _, _), _, _ = agent((y, z, s1), 1.0)   # second step consumes the emitted means
         (y2r, s2r, _, _), _, _ = agent((y.clone(), z, s1), 1.0)
         assert torch.equal(s2, s2r) and float((y2 - y2r).abs().max()) <= 1e-5
+
+
+# ----------------------------------------------------------------------------------------------
+# 8. differentiable replay: backward through a planned batch of pipelines
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("clip_each", [True, False])
+def test_backward_through_planned_pipelines(dev, clip_each):
+    """replay_grad.apply_plan: gradients w.r.t. the input image and w.r.t. EVERY step's parameters of
+    heterogeneous pipelines (per-pixel runs fused, one stencil step per phase, two-stencil pipelines
+    split into phases) against autograd through the CPU oracle; values equal execute_plan's."""
+    from adaptiveisp_b200 import replay
+    from adaptiveisp_b200.replay_grad import apply_plan
+    seqs = [
+        [O.OP_EXPOSURE, O.OP_GAMMA, O.OP_WB, O.OP_CCM, O.OP_SHARPEN],          # isp/filters.py:753-815
+        [O.OP_WNB, O.OP_NLM, O.OP_USM],                                        # BASELINE configs[3]: two phases
+        [O.OP_TONE, O.OP_USM, O.OP_CONTRAST, O.OP_SATPLUS],
+        [O.OP_CCM, O.OP_COLOR],
+        [O.OP_SHARPEN_V2],
+    ]
+    B, H, W = len(seqs), 24, 36
+    img, _, _, _, plist = _seq_case(seqs, H, W, seed=77)
+    plan = replay.plan_pipeline(seqs, plist, dev)
+    assert len(plan.phases) == 2
+    P = [ph.params.clone().requires_grad_(True) for ph in plan.phases]
+    xd = img.to(dev).requires_grad_(True)
+    g = cases.grad_out(img.shape, 77)
+    g[1].abs_()                                       # the NLM sample: see test_filter_matches_oracle
+    y = apply_plan(xd, plan, P, clip_each=clip_each)
+    (y * g.to(dev)).sum().backward()
+    fast = replay.execute_plan(img.to(dev), plan, clip_each=clip_each)
+    assert float((fast - y.detach()).abs().max()) <= 1e-6
+    segs = [replay.segment(s) for s in seqs]
+    chk = Checks()
+    for b, seq in enumerate(seqs):
+        xc = img[b:b + 1].clone().requires_grad_(True)
+        pcs = [p.clone().requires_grad_(True) for p in plist[b]]
+        yc = O.chain(seq, xc, pcs, clip_each)
+        (yc * g[b:b + 1]).sum().backward()
+        tag = f"sample {b} {[O.OP_NAMES[o] for o in seq]}"
+        tol_o, tol_g = 1e-5 * max(len(seq), 3), 1e-4 * max(len(seq), 3)
+        chk.out(y[b:b + 1].detach().cpu().numpy(), yc.detach().numpy(), tol_o, tag)
+        chk.norm(xd.grad[b:b + 1].cpu().numpy(), xc.grad.numpy(), tol_g, tag + " d/d img")
+        for phase, seg in enumerate(segs[b]):
+            for j, k in enumerate(seg):
+                n = O.OP_NPARAMS[seq[k]]
+                ref = pcs[k].grad.reshape(-1).numpy()
+                if np.abs(ref).max() > 1e-6:
+                    chk.grad(P[phase].grad[b, j, :n].cpu().numpy(), ref, tol_g, f"{tag} step {k}")
+    chk.done()
