@@ -48,6 +48,8 @@ SIGNATURES = {
     "aisp_select": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P,
                             _P, _P]),
     "aisp_select_bwd": (c_int, [_P, _P, c_int, c_int, _P, _P]),
+    "aisp_regress_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "aisp_regress_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "aisp_bank_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "aisp_bank_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
 }

@@ -101,6 +101,7 @@ class Agent(nn.Module):
         # filter index -> aisp_op code, as a device-side lookup table (no host sync per step)
         self.register_buffer("_op_table", torch.tensor([f.OP for f in self.filters], dtype=torch.int32),
                              persistent=False)
+        self._predictor = None
 
     # ------------------------------------------------------------------------------------------
     def downsample(self, x):
@@ -118,8 +119,17 @@ class Agent(nn.Module):
             return AF.block_mean(x, (oh, ow))
         return self.down_sample(x)
 
-    def predict_all_params(self, filter_features):
-        """Every filter's regressed parameters (tiny ``[B,n]`` tensors) packed as ``[B,F,PSTRIDE]``."""
+    def predict_all_params(self, filter_features, batched=True):
+        """Every filter's regressed parameters (tiny ``[B,n]`` tensors) packed as ``[B,F,PSTRIDE]``, plus the
+        per-filter tensors in the reference's layouts.  ``batched`` (default, CUDA): one GEMM for the ten
+        ``fc1`` layers + one regressor kernel (``filters.BankPredictor``); otherwise the per-module statement."""
+        if batched and filter_features.is_cuda:
+            if self._predictor is None:
+                from .filters import BankPredictor
+                self._predictor = BankPredictor(self.filters)
+            if self._predictor.usable(filter_features):
+                packed = self._predictor(filter_features)
+                return packed, self._predictor.split(packed)
         rows, per_filter = [], []
         for flt in self.filters:
             feats, _ = flt.extract_parameters(filter_features)

@@ -33,6 +33,8 @@ cudaError_t launch_nlm_seq_fwd(const float*, float*, const float*, const int32_t
                                cudaStream_t);
 cudaError_t launch_block_mean_masked(const float*, float*, int, int, int, int, int, const int32_t*, const int32_t*, int, int,
                                      cudaStream_t);
+cudaError_t launch_regress(const float*, const int32_t*, const int32_t*, int, int, int, const float*, float*, const float*,
+                           float*, cudaStream_t);
 bool pointwise_can_emit(int, int, int, int);
 bool sharpen_can_emit(int, int, int, int);
 int chain_bwd_max_steps();
@@ -256,6 +258,23 @@ int aisp_sequence_fwd(const float* img, float* out, const float* params, const i
         e = launch_block_mean_masked(out, down, B, H, W, down_h, down_w, ops, seq_len, S, families, st);
     }
     return (int)e;
+}
+
+// ---- feature -> parameter regressors of a whole filter bank, one launch each way
+int aisp_regress_fwd(const float* raw, const int32_t* filter_ops, const int32_t* offsets, int B, int F, int Ntot,
+                     const float* cfg_ranges, float* packed, void* stream) {
+    if (!raw || !filter_ops || !offsets || !cfg_ranges || !packed) return AISP_ERR_NULL;
+    if (B <= 0 || F <= 0 || Ntot <= 0 || (long long)B * F > (1LL << 30)) return AISP_ERR_SHAPE;
+    return (int)launch_regress(raw, filter_ops, offsets, B, F, Ntot, cfg_ranges, packed, nullptr, nullptr,
+                               (cudaStream_t)stream);
+}
+
+int aisp_regress_bwd(const float* raw, const float* grad_packed, const int32_t* filter_ops, const int32_t* offsets,
+                     int B, int F, int Ntot, const float* cfg_ranges, float* grad_raw, void* stream) {
+    if (!raw || !grad_packed || !filter_ops || !offsets || !cfg_ranges || !grad_raw) return AISP_ERR_NULL;
+    if (B <= 0 || F <= 0 || Ntot <= 0 || (long long)B * F > (1LL << 30)) return AISP_ERR_SHAPE;
+    return (int)launch_regress(raw, filter_ops, offsets, B, F, Ntot, cfg_ranges, nullptr, grad_packed, grad_raw,
+                               (cudaStream_t)stream);
 }
 
 // ---- filter bank: F filters applied to the SAME batch (agent.py:103-107 runs every cfg.filter on

@@ -98,6 +98,7 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
     __shared__ float sraw[SEQ ? AISP_MAX_STEPS : 1][kConst];
     __shared__ float ssc[SEQ ? AISP_MAX_STEPS : 1][kConst];
     __shared__ int ssop[SEQ ? AISP_MAX_STEPS : 1];
+    __shared__ int rownz[kNlmSmH];               // staged row holds a non-zero value (see the zero shortcut below)
     const int b = bank_sample(bm, blockIdx.z);   // filter-bank launches: see BankMap
     int pos = 0, len = 1;
     if (SEQ) {
@@ -122,6 +123,7 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
         int gy = y0 - kNlmHalo + row;
         gy = wide ? (gy < 0 ? gy + H : (gy >= H ? gy - H : gy)) : wrap(gy, H);
         const float* rp = src + (size_t)gy * W;
+        bool nz = false;
         for (int col = lane32; col < kNlmSmW; col += 32) {
             int gx = x0 - kNlmHalo + col;
             gx = wide ? (gx < 0 ? gx + W : (gx >= W ? gx - W : gx)) : wrap(gx, W);
@@ -137,7 +139,10 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
             sC[1][row][col] = g;
             sC[2][row][col] = bl;
             sY[row][col] = (0.299f * r + 0.587f * g) + 0.114f * bl;
+            nz |= (r != 0.f) | (g != 0.f) | (bl != 0.f);   // (NaN counts as non-zero)
         }
+        nz = __any_sync(0xffffffffu, nz);
+        if (lane32 == 0) rownz[row] = nz ? 1 : 0;
     }
     __syncthreads();
 
@@ -163,9 +168,18 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
 #pragma unroll
     for (int i = 0; i < kNlmRows / 2; ++i) { wsum2[i] = pack2(0.f, 0.f); wd2[i] = pack2(0.f, 0.f); }
 
+    // Zero shortcut.  LOD frames are letterboxed with EXACT-zero bars (dataset.py:834-838,887-888: a 3:2
+    // frame leaves a third of the 512 rows black), and wherever the whole 15 x 15 footprint of a warp's
+    // rows is zero every patch distance is 0, every weight exp(0) = 1 and the result is sum(0) / 121 = 0
+    // -- bit for bit what the 121-shift loop would produce -- so the warp skips the loop.  The test is
+    // warp-uniform (the loop's shuffles need every lane) and costs one flag per staged row.
+    bool live = false;
+    for (int t = 0; t < kNlmRows + 2 * kNlmHalo; ++t) live |= (rownz[r0 + t] != 0);
+    live = __any_sync(0xffffffffu, live);
+
     // source offsets run +5 .. -5 so that terms are accumulated in the reference's order
     // (x_shift outer, y_shift inner, shifted(p) = x(p - shift); denoise.py:106-109)
-    for (int dx = 5; dx >= -5; --dx) {
+    for (int dx = live ? 5 : -6; dx >= -5; --dx) {
         float ys[kNlmRows + 14];  // luma rows r0-7 .. r0+10 at column x0-2+lane+dx
 #pragma unroll
         for (int t = 0; t < kNlmRows + 14; ++t) ys[t] = sY[r0 + t][lane + dx + 5];
@@ -242,6 +256,10 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
     for (int i = 0; i < kNlmRows / 2; ++i) {
         wsum[2 * i] = lo2(wsum2[i]); wsum[2 * i + 1] = hi2(wsum2[i]);
         wd[2 * i] = lo2(wd2[i]); wd[2 * i + 1] = hi2(wd2[i]);
+    }
+    if (!live) {   // all 121 weights are exactly 1
+#pragma unroll
+        for (int i = 0; i < kNlmRows; ++i) wsum[i] = 121.0f;
     }
 #pragma unroll
     for (int i = 0; i < kNlmRows; ++i) {

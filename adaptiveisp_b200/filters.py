@@ -25,7 +25,7 @@ from . import functional as AF
 __all__ = [
     "Filter", "ExposureFilter", "GammaFilter", "ImprovedWhiteBalanceFilter", "ColorFilter", "ToneFilter",
     "ToneFilterV2", "ContrastFilter", "WNBFilter", "SaturationPlusFilter", "DenoiseFilter", "SharpenUSMFilter",
-    "SharpenFilter", "SharpenFilterV2", "CCMFilter", "FilterBank", "tanh01", "tanh_range", "lerp", "rgb2lum",
+    "SharpenFilter", "SharpenFilterV2", "CCMFilter", "FilterBank", "BankPredictor", "tanh01", "tanh_range", "lerp", "rgb2lum",
 ]
 
 
@@ -352,6 +352,59 @@ class CCMFilter(Filter):  # isp/filters.py:694-708
         return tanh_range(*self.cfg.ccm_range)(features)
 
 
+class BankPredictor:
+    """Features -> packed parameter rows ``[B,F,PSTRIDE]`` for a list of filter modules in a handful of
+    launches: ONE GEMM for all ``fc1`` layers (their weights concatenated on the fly -- the modules keep
+    their own parameters, so ``state_dict`` and the gradients are the per-module ones), the F small
+    ``fc_filter`` GEMMs, and ONE kernel for every filter's ``filter_param_regressor``
+    (``aisp_regress_fwd``; one more in backward).  The per-module statement (``extract_parameters`` +
+    ``filter_param_regressor``: ~25 launches per filter and as many again in backward) stays available
+    and is what this is tested against; ``fc_mask`` is not evaluated (its output is never used:
+    isp/filters.py:161-173) and its parameters get no gradient, as in the reference."""
+
+    def __init__(self, filters):
+        self.filters = list(filters)
+        self.ops = [int(f.OP) for f in self.filters]
+        self.n = [int(f.get_num_filter_parameters()) for f in self.filters]
+        self.offsets = [sum(self.n[:i]) for i in range(len(self.n))]
+        self._dev = {}
+        self._cfg_c = AF.regress_ranges(self.filters[0].cfg)
+
+    def usable(self, features) -> bool:
+        return features.is_cuda and features.dtype == torch.float32 and all(f.predict for f in self.filters)
+
+    def _tables(self, device):
+        t = self._dev.get(device)
+        if t is None:
+            t = (torch.tensor(self.ops, dtype=torch.int32, device=device),
+                 torch.tensor(self.offsets, dtype=torch.int32, device=device))
+            self._dev[device] = t
+        return t
+
+    def __call__(self, features):
+        fl = self.filters
+        F, B = len(fl), features.shape[0]
+        w1 = torch.cat([f.fc1.weight for f in fl], dim=0)
+        b1 = torch.cat([f.fc1.bias for f in fl], dim=0)
+        hidden = nn.functional.leaky_relu(nn.functional.linear(features, w1, b1), 0.2).view(B, F, -1)
+        raw = torch.cat([nn.functional.linear(hidden[:, i], f.fc_filter.weight, f.fc_filter.bias)
+                         for i, f in enumerate(fl)], dim=1)
+        fops, offs = self._tables(features.device)
+        return AF.regress(raw, fops, offs, self._cfg_c, F)
+
+    def split(self, packed):
+        """Packed rows -> the per-filter parameter tensors in the reference's own layouts (views)."""
+        out = []
+        for i, f in enumerate(self.filters):
+            p = packed[:, i, :self.n[i]]
+            if f.OP == AF.OP_TONE:
+                p = p.reshape(-1, 8, 1, 1, 1)
+            elif f.OP == AF.OP_COLOR:
+                p = p.reshape(-1, 8, 3, 1, 1)
+            out.append(p)
+        return out
+
+
 class FilterBank:
     """Every filter of a list applied to the same batch in one banked launch set.
 
@@ -360,8 +413,8 @@ class FilterBank:
         stack = torch.stack([f(img, img_features)[0] for f in filters], dim=1)      # [B,F,3,H,W]
 
     but the image arithmetic of all F filters is three kernel launches (``functional.apply_bank``)
-    instead of F, and the image is fetched from HBM once.  Parameter regression stays per filter
-    (the FC layers differ); ``filters`` are the already constructed drop-in modules, so their
+    instead of F, the image is fetched from HBM once, and the parameter prediction of all F filters is
+    batched (:class:`BankPredictor`).  ``filters`` are the already constructed drop-in modules, so their
     weights / ``state_dict`` are untouched.  Not an ``nn.Module``: it owns no parameters.
     """
 
@@ -373,9 +426,11 @@ class FilterBank:
             if f.use_masking():
                 raise NotImplementedError("spatial masking is dead code in the reference and is not part of the hot path")
         self.ops = [int(f.OP) for f in self.filters]
+        self.predictor = BankPredictor(self.filters)
 
     def parameters_for(self, img_features=None, specified_parameters=None):
-        """-> list of per-filter parameter tensors in the reference's own layouts."""
+        """-> list of per-filter parameter tensors in the reference's own layouts (the per-module
+        statement: ``extract_parameters`` + ``filter_param_regressor`` of every filter)."""
         assert (img_features is None) ^ (specified_parameters is None)
         if specified_parameters is not None:
             assert len(specified_parameters) == len(self.filters)
@@ -386,10 +441,18 @@ class FilterBank:
             out.append(f.filter_param_regressor(feats))
         return out
 
-    def __call__(self, img, img_features=None, specified_parameters=None, clip=True):
-        """-> (stack ``[B,F,3,H,W]``, list of debug_info dicts as ``Filter.forward`` returns them)."""
+    def packed_parameters(self, img_features=None, specified_parameters=None, batched=True):
+        """-> (``P [B,F,PSTRIDE]``, per-filter parameter tensors)."""
+        if img_features is not None and batched and self.predictor.usable(img_features):
+            P = self.predictor(img_features)
+            return P, self.predictor.split(P)
         params = self.parameters_for(img_features, specified_parameters)
         P = torch.stack([AF.pack_params(p, f.get_num_filter_parameters()) for p, f in zip(params, self.filters)], dim=1)
+        return P, params
+
+    def __call__(self, img, img_features=None, specified_parameters=None, clip=True, batched=True):
+        """-> (stack ``[B,F,3,H,W]``, list of debug_info dicts as ``Filter.forward`` returns them)."""
+        P, params = self.packed_parameters(img_features, specified_parameters, batched)
         stack = AF.apply_bank(img, P, self.ops, clip=clip)
         debug = []
         for p, f in zip(params, self.filters):

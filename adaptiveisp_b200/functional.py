@@ -258,6 +258,60 @@ def apply_bank(img: torch.Tensor, P: torch.Tensor, ops: Sequence[int], clip: boo
     return _ApplyBank.apply(img, P.contiguous(), ops, clip)
 
 
+class _Regress(torch.autograd.Function):
+    """raw fc_filter outputs of a whole bank [B,Ntot] -> packed parameter rows [B,F,PSTRIDE], one launch each
+    way (``aisp_regress_fwd/bwd``): every filter's ``filter_param_regressor`` (isp/filters.py:215-708)."""
+
+    @staticmethod
+    def forward(ctx, raw, fops, offs, cfg_c, F: int):
+        if not raw.is_cuda or raw.dtype != torch.float32 or raw.dim() != 2:
+            raise _lib.AispError("regress: raw features must be a CUDA float32 [B,Ntot] tensor")
+        raw = raw.contiguous()
+        B, Ntot = raw.shape
+        packed = torch.empty((B, F, PSTRIDE), dtype=torch.float32, device=raw.device)
+        with torch.cuda.device(raw.device):
+            rc = _lib.lib().aisp_regress_fwd(raw.data_ptr(), fops.data_ptr(), offs.data_ptr(), B, F, Ntot, cfg_c,
+                                             packed.data_ptr(), _lib.stream_ptr(raw.device))
+        _lib.check(rc, "aisp_regress_fwd")
+        ctx.save_for_backward(raw, fops, offs)
+        ctx.cfg_c, ctx.F = cfg_c, F
+        return packed
+
+    @staticmethod
+    def backward(ctx, g):
+        raw, fops, offs = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None, None
+        B, Ntot = raw.shape
+        g = g.contiguous()
+        graw = torch.empty_like(raw)
+        with torch.cuda.device(raw.device):
+            rc = _lib.lib().aisp_regress_bwd(raw.data_ptr(), g.data_ptr(), fops.data_ptr(), offs.data_ptr(), B, ctx.F,
+                                             Ntot, ctx.cfg_c, graw.data_ptr(), _lib.stream_ptr(raw.device))
+        _lib.check(rc, "aisp_regress_bwd")
+        return graw, None, None, None, None
+
+
+def regress_ranges(cfg):
+    """The 15 floats of ``aisp_regress_*``'s ``cfg_ranges``: (lo, span) pairs formed in Python floats exactly as
+    the reference's ``tanh_range(l, r, initial)`` forms ``r - l`` and its ``atanh`` shift (isp/filters.py:27-34)."""
+    import math
+    lg = math.log(cfg.gamma_range)
+    cl, ch = cfg.color_curve_range
+    vals = [-cfg.exposure_range, cfg.exposure_range - (-cfg.exposure_range), -lg, lg - (-lg),
+            cfg.tone_curve_range[0], cfg.tone_curve_range[1] - cfg.tone_curve_range[0],
+            cl, ch - cl, math.atanh(2 * (1 - cl) / (ch - cl) - 1),
+            cfg.usm_sharpen_range[0], cfg.usm_sharpen_range[1] - cfg.usm_sharpen_range[0],
+            cfg.sharpen_range[0], cfg.sharpen_range[1] - cfg.sharpen_range[0],
+            cfg.ccm_range[0], cfg.ccm_range[1] - cfg.ccm_range[0]]
+    return (ctypes.c_float * 15)(*[float(v) for v in vals])
+
+
+def regress(raw: torch.Tensor, fops: torch.Tensor, offs: torch.Tensor, cfg_c, F: int) -> torch.Tensor:
+    """Differentiable: ``raw`` [B,Ntot] -> packed [B,F,PSTRIDE] (see :class:`_Regress`)."""
+    return _Regress.apply(raw, fops, offs, cfg_c, F)
+
+
 SELECT_SAMPLE, SELECT_ARGMAX, SELECT_FORCED = 0, 1, 2   # enum aisp_select_mode
 
 

@@ -255,6 +255,24 @@ int aisp_select_bwd(const float* grad_rows, const int64_t* sel, int B, int F, fl
                     void* stream);
 
 /*
+ * Feature -> parameter regressors of every filter of a bank in ONE launch (forward) and one (backward):
+ * `Filter.filter_param_regressor` of isp/filters.py:215-708 (tanh_range / exp / sigmoid, the white-balance
+ * red-feature mask and luminance normalisation :253-272), producing the packed rows the image kernels read.
+ *   raw         [B,Ntot]  the fc_filter outputs of the F filters side by side; filter f's n_f features
+ *                         start at column offsets[f]
+ *   filter_ops  [F] int32 (device)   offsets [F] int32 (device)
+ *   cfg_ranges  HOST array of 15 floats, (lo, span) pairs formed in double precision as the reference
+ *               forms r - l: exposure, log-gamma, tone curve, colour curve, colour-curve shift
+ *               (atanh term of tanh_range's `initial`), USM, sharpen, CCM
+ *   packed      [B,F,AISP_PSTRIDE]   (unused tail of a row: zeros)
+ * Backward: grad_raw [B,Ntot] = J^T grad_packed (columns of no filter are left untouched).
+ */
+int aisp_regress_fwd(const float* raw, const int32_t* filter_ops, const int32_t* offsets, int B, int F, int Ntot,
+                     const float* cfg_ranges, float* packed, void* stream);
+int aisp_regress_bwd(const float* raw, const float* grad_packed, const int32_t* filter_ops, const int32_t* offsets,
+                     int B, int F, int Ntot, const float* cfg_ranges, float* grad_raw, void* stream);
+
+/*
  * Filter bank: apply F filters to the SAME batch and keep every result -- the stack of
  * agent.py:103-107 (`filtered_images.append(filter(...))` for every cfg.filter, then
  * torch.stack(dim=1)), which is also BASELINE.json configs[1] ("all 10 filters fwd+bwd").

@@ -704,3 +704,52 @@ def test_backward_through_planned_pipelines(dev, clip_each):
                 if np.abs(ref).max() > 1e-6:
                     chk.grad(P[phase].grad[b, j, :n].cpu().numpy(), ref, tol_g, f"{tag} step {k}")
     chk.done()
+
+
+# ----------------------------------------------------------------------------------------------
+# 9. batched parameter prediction: one fc1 GEMM + one regressor kernel for the whole bank
+# ----------------------------------------------------------------------------------------------
+def test_batched_parameter_prediction_matches_the_modules(F, cfg, dev):
+    """filters.BankPredictor (what Agent.forward and FilterBank use) against the per-module statement
+    `extract_parameters` + `filter_param_regressor` of every drop-in class (all 13: cfg.filters plus
+    USM, ColorFilter, SharpenFilterV2): parameters, and the gradients that reach each module's own
+    fc1 / fc_filter weights; fc_mask gets none."""
+    torch.manual_seed(7)
+    classes = list(cfg.filters) + [F.SharpenUSMFilter, F.ColorFilter, F.SharpenFilterV2]
+    mods = [c(cfg, predict=True).to(dev) for c in classes]
+    B = 9
+    feats = (torch.randn((B, cfg.feature_extractor_dims), device=dev) * 0.3).requires_grad_(True)
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        pred = F.BankPredictor(mods)
+        P = pred(feats)
+        gP = torch.randn(P.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+        (P * gP).sum().backward()
+        got_w = [(m.fc1.weight.grad.clone(), m.fc_filter.weight.grad.clone(), m.fc_filter.bias.grad.clone()) for m in mods]
+        got_f = feats.grad.clone()
+        assert all(m.fc_mask.weight.grad is None for m in mods)
+        for m in mods:
+            m.zero_grad(set_to_none=True)
+        feats.grad = None
+        loss = 0.0
+        for i, m in enumerate(mods):
+            raw, _ = m.extract_parameters(feats)
+            p = m.filter_param_regressor(raw)
+            n = m.get_num_filter_parameters()
+            flat = p.reshape(B, n)
+            assert float((P[:, i, :n] - flat).abs().max()) <= 2e-6, m.get_short_name()
+            assert float(P[:, i, n:].abs().max()) == 0.0 if n < 24 else True
+            loss = loss + (flat * gP[:, i, :n]).sum()
+        loss.backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    for m, (g1, gw, gb) in zip(mods, got_w):
+        tag = m.get_short_name()
+        assert rel_err(g1.cpu().numpy(), m.fc1.weight.grad.cpu().numpy()) <= 1e-4, tag
+        assert rel_err(gw.cpu().numpy(), m.fc_filter.weight.grad.cpu().numpy()) <= 1e-4, tag
+        assert rel_err(gb.cpu().numpy(), m.fc_filter.bias.grad.cpu().numpy()) <= 1e-4, tag
+    assert rel_err(got_f.cpu().numpy(), feats.grad.cpu().numpy()) <= 1e-4
+    # the reference layouts come back as views of the packed rows
+    per = pred.split(P)
+    assert per[classes.index(F.ToneFilter)].shape == (B, 8, 1, 1, 1) and per[classes.index(F.ColorFilter)].shape == (B, 8, 3, 1, 1)
