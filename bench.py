@@ -484,7 +484,7 @@ def run_b200(args):
         stack.backward(gout_all)
         return stack[:, nf - 1].contiguous()
 
-    graphed = GraphedHostLoop(lambda x, ft: isp_step(x, ft).detach(), (img, feats * 0.05), modules=flts)
+    graphed = GraphedHostLoop(lambda x, ft: isp_step(x, ft).detach(), (img, feats * 0.05), modules=flts, slots=3)
 
     def e2e_run(nsteps, mode):
         """`nsteps` steps, each uploading the image batch + features from pinned host memory and
