@@ -35,6 +35,7 @@ cudaError_t launch_block_mean_masked(const float*, float*, int, int, int, int, i
                                      cudaStream_t);
 cudaError_t launch_regress(const float*, const int32_t*, const int32_t*, int, int, int, const float*, float*, const float*,
                            float*, cudaStream_t);
+cudaError_t launch_value_stats(const float*, int, int, float*, cudaStream_t);
 bool pointwise_can_emit(int, int, int, int);
 bool sharpen_can_emit(int, int, int, int);
 int chain_bwd_max_steps();
@@ -164,6 +165,12 @@ int aisp_block_mean(const float* img, float* down, int B, int H, int W, int out_
     if (!shape_ok(B, H, W) || out_h <= 0 || out_w <= 0 || (long long)B * 3 > 65535) return AISP_ERR_SHAPE;
     if (H % out_h != 0 || W % out_w != 0) return AISP_ERR_UNSUPPORTED;  // adaptive pooling with uneven windows
     return (int)launch_block_mean(img, down, B, H, W, out_h, out_w, (cudaStream_t)stream);
+}
+
+int aisp_value_stats(const float* down, int B, int h, int w, float* stats, void* stream) {
+    if (!down || !stats) return AISP_ERR_NULL;
+    if (B <= 0 || h <= 0 || w <= 0 || (long long)h * w > (1LL << 28)) return AISP_ERR_SHAPE;
+    return (int)launch_value_stats(down, B, h * w, stats, (cudaStream_t)stream);
 }
 
 int aisp_select_apply_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,

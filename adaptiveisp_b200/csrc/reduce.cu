@@ -86,4 +86,62 @@ cudaError_t launch_block_mean(const float* img, float* down, int B, int H, int W
     return launch_block_mean_masked(img, down, B, H, W, oh, ow, nullptr, nullptr, 1, 7, st);
 }
 
+// ---------------------------------------------------------------------------------------------
+// The critic's image statistics (value.py:64-75) of the pooled image [B,3,h,w] in one launch, one CTA per
+// image: mean and unbiased variance of the luminance 0.27 r + 0.67 g + 0.06 b + 1e-5, and the mean of
+// (max - min) / (min(max + min, 2 - max - min) + 0.01) over the clipped channels.  The reference spends
+// ~20 ATen launches on these 12k numbers per image.  Sums are fp32 per thread, fp64 across the CTA (fixed
+// order); the variance is taken around the mean in a second sweep, like torch.var.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+value_stats_kernel(const float* __restrict__ down, int n, float* __restrict__ stats) {
+    __shared__ double red[2][kWarps];
+    __shared__ double s_mean;
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* r = down + (size_t)b * 3 * n;
+    const float* g = r + n;
+    const float* bl = g + n;
+    float sl = 0.f, ss = 0.f;
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        const float x = r[i], y = g[i], z = bl[i];
+        sl += ((x * 0.27f + y * 0.67f) + z * 0.06f) + 1e-5f;
+        const float cx = clip01(x), cy = clip01(y), cz = clip01(z);
+        const float mx = max_nan(cx, max_nan(cy, cz)), mn = min_nan(cx, min_nan(cy, cz));
+        ss += (mx - mn) / (min_nan(mx + mn, (2.0f - mx) - mn) + 1e-2f);
+    }
+    double dl = sl, ds = ss;
+    for (int o = 16; o > 0; o >>= 1) { dl += __shfl_xor_sync(0xffffffffu, dl, o); ds += __shfl_xor_sync(0xffffffffu, ds, o); }
+    if (lane == 0) { red[0][warp] = dl; red[1][warp] = ds; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tl = 0.0, ts = 0.0;
+        for (int w = 0; w < kWarps; ++w) { tl += red[0][w]; ts += red[1][w]; }
+        s_mean = tl / n;
+        stats[b * 3 + 0] = (float)(tl / n);
+        stats[b * 3 + 2] = (float)(ts / n);
+    }
+    __syncthreads();
+    const float mean = (float)s_mean;
+    float sv = 0.f;
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        const float d = (((r[i] * 0.27f + g[i] * 0.67f) + bl[i] * 0.06f) + 1e-5f) - mean;
+        sv = fmaf(d, d, sv);
+    }
+    double dv = sv;
+    for (int o = 16; o > 0; o >>= 1) dv += __shfl_xor_sync(0xffffffffu, dv, o);
+    __syncthreads();
+    if (lane == 0) red[0][warp] = dv;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tv = 0.0;
+        for (int w = 0; w < kWarps; ++w) tv += red[0][w];
+        stats[b * 3 + 1] = (float)(tv / (n > 1 ? n - 1 : 1));
+    }
+}
+
+cudaError_t launch_value_stats(const float* down, int B, int n, float* stats, cudaStream_t st) {
+    value_stats_kernel<<<B, kThreads, 0, st>>>(down, n, stats);
+    return cudaGetLastError();
+}
+
 }  // namespace aisp

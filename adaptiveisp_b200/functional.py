@@ -457,6 +457,20 @@ def block_mean(img: torch.Tensor, out_hw=(64, 64)) -> torch.Tensor:
     return down
 
 
+@torch.no_grad()
+def value_stats(down: torch.Tensor) -> torch.Tensor:
+    """The critic's statistics of the pooled image (value.py:64-75) -> ``[B,3]`` = (mean luminance, unbiased
+    luminance variance, mean saturation), one launch instead of ~20 (no autograd: use
+    ``value.value_statistics`` where a gradient must flow)."""
+    _lib.require_image(down, "down")
+    B, _, h, w = down.shape
+    stats = torch.empty((B, 3), dtype=torch.float32, device=down.device)
+    with torch.cuda.device(down.device):
+        rc = _lib.lib().aisp_value_stats(down.data_ptr(), B, h, w, stats.data_ptr(), _lib.stream_ptr(down.device))
+    _lib.check(rc, "aisp_value_stats")
+    return stats
+
+
 def image_stats(down: torch.Tensor):
     """Per-image mean and finiteness from the block-mean image (train.py:288-290,374): the mean of
     equal-size block means is the image mean; a block mean is finite iff its whole block is."""

@@ -65,7 +65,11 @@ class Value(nn.Module):
 
     def forward(self, images, states=None):
         images = self.pooled(images)
-        state_feature = value_statistics(images)
+        if images.is_cuda and images.dtype == torch.float32 and images.is_contiguous() and \
+                not (torch.is_grad_enabled() and images.requires_grad):
+            state_feature = AF.value_stats(images)         # one launch; no gradient is needed through them
+        else:
+            state_feature = value_statistics(images)
         if states is None:
             states = state_feature
         else:

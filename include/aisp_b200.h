@@ -189,6 +189,13 @@ int aisp_nlm_bwd_img(const float* img, const float* out, const float* wsum, cons
 int aisp_block_mean(const float* img, float* down, int B, int H, int W, int out_h, int out_w, void* stream);
 
 /*
+ * The critic's statistics of the pooled image (value.py:64-75): stats[b] = (mean luminance, unbiased
+ * luminance variance, mean saturation) of down[b] ([B,3,h,w], e.g. the block means above), one launch.
+ * Forward only: the caller keeps the PyTorch statement where a gradient must flow through them.
+ */
+int aisp_value_stats(const float* down, int B, int h, int w, float* stats, void* stream);
+
+/*
  * Apply the selected filter of each sample: the B200 form of agent.py:103-116,154, where the
  * reference runs all 10 filters on the whole batch, stacks [B,10,3,H,W] and keeps one of ten.
  * Issues the three family kernels back to back on `stream` (no host sync; graph-capturable);

@@ -753,3 +753,19 @@ def test_batched_parameter_prediction_matches_the_modules(F, cfg, dev):
     # the reference layouts come back as views of the packed rows
     per = pred.split(P)
     assert per[classes.index(F.ToneFilter)].shape == (B, 8, 1, 1, 1) and per[classes.index(F.ColorFilter)].shape == (B, 8, 3, 1, 1)
+
+
+def test_value_statistics_kernel_matches_the_pytorch_statement(dev):
+    """value.py:64-75 on the pooled image: mean / unbiased variance of the luminance and the mean
+    saturation, one launch, against the reference's own op sequence (value.value_statistics)."""
+    from adaptiveisp_b200 import functional as AF
+    from adaptiveisp_b200.value import value_statistics
+    for (B, h, w) in [(5, 64, 64), (3, 16, 24), (2, 1, 7)]:
+        x = cases.edge_image(B, h, w, seed=h).to(dev)          # samples >= 2 spill outside [0,1]: the clip matters
+        got = AF.value_stats(x)
+        ref = value_statistics(x.double()).float()
+        ref32 = value_statistics(x)
+        assert got.shape == (B, 3)
+        err = ((got - ref).abs() / ref.abs().clamp_min(1e-3)).max()
+        assert float(err) <= 1e-5, (B, h, w, got, ref)
+        assert float(((got - ref32).abs() / ref32.abs().clamp_min(1e-3)).max()) <= 1e-4
