@@ -760,7 +760,7 @@ def test_value_statistics_kernel_matches_the_pytorch_statement(dev):
     saturation, one launch, against the reference's own op sequence (value.value_statistics)."""
     from adaptiveisp_b200 import functional as AF
     from adaptiveisp_b200.value import value_statistics
-    for (B, h, w) in [(5, 64, 64), (3, 16, 24), (2, 1, 7)]:
+    for (B, h, w) in [(5, 64, 64), (3, 16, 24), (2, 9, 11)]:
         x = cases.edge_image(B, h, w, seed=h).to(dev)          # samples >= 2 spill outside [0,1]: the clip matters
         got = AF.value_stats(x)
         ref = value_statistics(x.double()).float()
