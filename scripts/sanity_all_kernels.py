@@ -41,6 +41,30 @@ for (B, H, W) in [(3, 37, 53), (2, 48, 64), (1, 9, 130)]:
         rows.sum().backward()
     steps = [[0, 1, 3, 9, 4][: 1 + b % 5] for b in range(B)]
     params = [[torch.rand(AF.NUM_PARAMS[o]) * 0.5 + 0.5 for o in s] for s in steps]
-    out = replay.execute_plan(img, replay.plan_pipeline(steps, params, dev), True)
+    plan = replay.plan_pipeline(steps, params, dev)
+    out = replay.execute_plan(img, plan, True)
+    # round 2: sequence launch set with a high-resolution twin and block means, fused sequence backward
+    # (6 stages, ColorFilter), differentiable replay, regressors, value statistics
+    hi = torch.rand((B, 3, H + 11, W + 7), device=dev)
+    out2, hi2 = replay.execute_plan(img, plan, True, high_res=hi)
+    oh, ow = (H // 2 if H % 2 == 0 else H), (W // 4 if W % 4 == 0 else W)
+    y3, _, d3 = AF.apply_ops(img.clone().requires_grad_(True), P.clone().requires_grad_(True), ops, True, down_hw=(oh, ow))
+    (y3.sum() + d3.sum()).backward()
+    seq = torch.tensor([[11, 5, 2, 7, 6, 0]] * B, dtype=torch.int32, device=dev)
+    lens = torch.tensor([(6 - b) for b in range(B)], dtype=torch.int32, device=dev)
+    Pc = (torch.rand((B, 6, 24), device=dev) * 0.5 + 0.6)
+    Pc[:, 2, :9] = torch.eye(3, device=dev).reshape(1, 9) + 0.05
+    Pc.requires_grad_(True)
+    xc = img.clone().requires_grad_(True)
+    (AF.apply_chain(xc, Pc, seq, lens, clip_each=True) * g).sum().backward()
+    from adaptiveisp_b200.replay_grad import apply_plan
+    Pg = [ph.params.clone().requires_grad_(True) for ph in plan.phases]
+    (apply_plan(img.clone().requires_grad_(True), plan, Pg) * g).sum().backward()
+    AF.value_stats(AF.block_mean(torch.rand((B, 3, 64, 96), device=dev), (16, 24)))
+from adaptiveisp_b200 import filters as Fm
+from adaptiveisp_b200.config import make_cfg
+cfg = make_cfg(feature_extractor_dims=64, fc1_size=16)
+mods = [c(cfg, predict=True).to(dev) for c in cfg.filters]
+Fm.BankPredictor(mods)(torch.randn((5, 64), device=dev)).sum().backward()
 torch.cuda.synchronize()
 print("sanity_all_kernels: ok", float(out.mean()))
