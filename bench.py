@@ -57,8 +57,20 @@ NCU_TRAFFIC_BYTES = {"NLM": 550.5e6, "pw_fwd": 352.9e6, "pw_bwd": 410.6e6, "shar
 NLM_INSTR_PER_PXSHIFT, NLM_LANE_EFF = 959.0 / 44.0, 28.0 / 32.0
 
 
-def nlm_issue_bound(fwd_ms, npx, sm_mhz):
+def nlm_active_fraction(img):
+    """Fraction of the kernel's 4-row warp groups that run the 121-shift loop: a group whose whole footprint
+    (rows r0-7 .. r0+10, circular) is exactly zero takes the zero shortcut."""
+    Hh = img.shape[2]
+    rownz = (img.abs().amax(dim=(1, 3)) > 0)                      # [B,H]
+    live = torch.zeros((img.shape[0], Hh // 4), dtype=torch.bool, device=img.device)
+    for d in range(-7, 11):
+        live |= torch.roll(rownz, shifts=-d, dims=1)[:, 0:Hh - Hh % 4:4]
+    return float(live.float().mean())
+
+
+def nlm_issue_bound(fwd_ms, npx, sm_mhz, active=1.0):
     """NLM against the bound that actually limits it: warp-instruction issue (4 per clock per SM)."""
+    npx = npx * active
     thread_instr = npx * 121 * NLM_INSTR_PER_PXSHIFT / NLM_LANE_EFF
     ideal_ms = thread_instr / (148 * 128 * sm_mhz * 1e6) * 1e3
     # SURVEY 8(d)'s bound for this kernel: >= 121 sqrt + 121 exp per pixel on 16 MUFU lanes per SM and clock
@@ -66,8 +78,10 @@ def nlm_issue_bound(fwd_ms, npx, sm_mhz):
     return {"ideal_ms_at_full_issue_rate": round(ideal_ms, 3), "measured_ms": round(fwd_ms, 3),
             "frac": round(ideal_ms / fwd_ms, 3), "sm_mhz": sm_mhz,
             "mufu_bound_ms": round(mufu_ms, 3), "frac_of_mufu_bound": round(mufu_ms / fwd_ms, 3),
-            "model": "B*H*W*121 shifts * 21.8 SASS instr / (28/32 lanes) / (148 SMs * 128 thread-instr/clk); "
-                     "MUFU bound: 242 MUFU ops per pixel / (148 SMs * 16 lanes/clk)"}
+            "active_pixel_fraction": round(active, 4),
+            "model": "active pixels * 121 shifts * 21.8 SASS instr / (28/32 lanes) / (148 SMs * 128 thread-instr/clk); "
+                     "MUFU bound: 242 MUFU ops per active pixel / (148 SMs * 16 lanes/clk); active pixels = those whose "
+                     "warp group does not take the all-zero-footprint shortcut (letterbox bars)"}
 
 
 def clk_mhz(clocks):
@@ -640,7 +654,8 @@ def run_b200(args):
                          "note": "NLM is SM-issue/FP32/MUFU-bound by construction (121 patch distances, sqrt and exp "
                                  "per pixel), not HBM-bound: see 'issue_bound' and DESIGN.md 4.3; the HBM fractions "
                                  "of the HBM-bound kernels are in 'kernels' / 'hbm_frac_excl_nlm'",
-                         "issue_bound": nlm_issue_bound(kern["NLM"][0], npx, (clocks.samples and clk_mhz(clocks)) or 1965.0)
+                         "issue_bound": nlm_issue_bound(kern["NLM"][0], npx, (clocks.samples and clk_mhz(clocks)) or 1965.0,
+                                                        nlm_active_fraction(img))
                          if "NLM" in kern else None},
             "step_segments_ms": {"bank_fwd": round(seg_fwd, 4), "bank_bwd": round(seg_bwd, 4),
                                  "unbanked_per_filter_sum": round(sum(k["fwd_ms"] + k["bwd_ms"] for k in klist), 4)},
