@@ -115,19 +115,39 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
     const size_t sb = (size_t)(b / bm.F);        // stashes stay compact: one NLM slot per image
 
     // stage clipped RGB and luma of the wrapped tile + halo       (isp/filters.py:583, denoise.py:11-17)
-    // a warp walks whole rows (row wrap once per row, column wrap by one conditional add when the
-    // image is wider than the tile footprint; the generic modulo only serves tiny images)
+    // The staged region is walked as ONE flat index range, fully unrolled: a thread's (up to) eight
+    // elements x three planes are independent loads that are all in flight together -- one or two L2 round
+    // trips per CTA instead of one per (row, column-pass) of a warp-per-row walk.  Row wrap / column wrap
+    // by conditional adds when the image is larger than the tile footprint; the generic modulo only serves
+    // tiny images.
     const int lane32 = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool wide = (W >= kNlmSmW) && (H >= kNlmSmH);
-    for (int row = warp; row < kNlmSmH; row += kWarps) {
-        int gy = y0 - kNlmHalo + row;
-        gy = wide ? (gy < 0 ? gy + H : (gy >= H ? gy - H : gy)) : wrap(gy, H);
-        const float* rp = src + (size_t)gy * W;
-        bool nz = false;
-        for (int col = lane32; col < kNlmSmW; col += 32) {
-            int gx = x0 - kNlmHalo + col;
-            gx = wide ? (gx < 0 ? gx + W : (gx >= W ? gx - W : gx)) : wrap(gx, W);
-            float r = __ldg(rp + gx), g = __ldg(rp + plane + gx), bl = __ldg(rp + 2 * plane + gx);
+    constexpr int kStageN = kNlmSmH * kNlmSmW;
+    constexpr int kStageIt = (kStageN + kThreads - 1) / kThreads;
+    if (threadIdx.x < kNlmSmH) rownz[threadIdx.x] = 0;
+    __syncthreads();
+    {
+        float vr[kStageIt], vg[kStageIt], vb[kStageIt];
+#pragma unroll
+        for (int it = 0; it < kStageIt; ++it) {
+            const int e = it * kThreads + threadIdx.x;
+            vr[it] = vg[it] = vb[it] = 0.f;
+            if (e < kStageN) {
+                const int row = e / kNlmSmW, col = e - row * kNlmSmW;
+                int gy = y0 - kNlmHalo + row, gx = x0 - kNlmHalo + col;
+                gy = wide ? (gy < 0 ? gy + H : (gy >= H ? gy - H : gy)) : wrap(gy, H);
+                gx = wide ? (gx < 0 ? gx + W : (gx >= W ? gx - W : gx)) : wrap(gx, W);
+                const float* rp = src + (size_t)gy * W + gx;
+                vr[it] = __ldg(rp);
+                vg[it] = __ldg(rp + plane);
+                vb[it] = __ldg(rp + 2 * plane);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < kStageIt; ++it) {
+            const int e = it * kThreads + threadIdx.x;
+            const int row = e / kNlmSmW, col = e - row * kNlmSmW;
+            float r = vr[it], g = vg[it], bl = vb[it];
             if (SEQ) {
                 for (int k = 0; k < pos; ++k) {
                     fwd_px<true>(ssop[k], ssc[k], r, g, bl);
@@ -135,14 +155,20 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
                 }
             }
             r = clip01(r); g = clip01(g); bl = clip01(bl);
-            sC[0][row][col] = r;
-            sC[1][row][col] = g;
-            sC[2][row][col] = bl;
-            sY[row][col] = (0.299f * r + 0.587f * g) + 0.114f * bl;
-            nz |= (r != 0.f) | (g != 0.f) | (bl != 0.f);   // (NaN counts as non-zero)
+            const bool in = e < kStageN;
+            if (in) {
+                sC[0][row][col] = r;
+                sC[1][row][col] = g;
+                sC[2][row][col] = bl;
+                sY[row][col] = (0.299f * r + 0.587f * g) + 0.114f * bl;
+            }
+            // "this staged row holds a non-zero value" (NaN counts): the lanes of a warp that staged the same
+            // row vote, the lowest of them ORs the flag in (a warp's 32 consecutive elements span 2-3 rows)
+            const bool nz = in && ((r != 0.f) | (g != 0.f) | (bl != 0.f));
+            const unsigned any = __ballot_sync(0xffffffffu, nz);
+            const unsigned grp = __match_any_sync(0xffffffffu, in ? row : -1);
+            if (in && (any & grp) && lane32 == __ffs(grp) - 1) atomicOr(&rownz[row], 1);
         }
-        nz = __any_sync(0xffffffffu, nz);
-        if (lane32 == 0) rownz[row] = nz ? 1 : 0;
     }
     __syncthreads();
 
