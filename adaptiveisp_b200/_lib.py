@@ -46,6 +46,8 @@ SIGNATURES = {
                                       _P]),
     "aisp_sequence_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, c_int,
                                   c_int, _P, _P, _P]),
+    "aisp_select_apply_bwd_pooled": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P,
+                                             _P, _P, c_size_t, _P]),
     "aisp_select": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P,
                             _P, _P]),
     "aisp_select_bwd": (c_int, [_P, _P, c_int, c_int, _P, _P]),

@@ -256,6 +256,22 @@ __device__ __forceinline__ void block_reduce_store(float (&acc)[N], float* red /
 
 enum { FAMILY_POINTWISE = 0, FAMILY_SHARPEN = 1, FAMILY_NLM = 2 };
 
+// Gradient that reaches the BLOCK MEANS of an output image (the critic pools the retouched image,
+// value.py:63, so train.py:341-342 sends a gradient into the pooled image as well as into the full one).
+// d mean / d pixel = 1 / (bh * bw): the backward kernels add g[b, ch, y >> bhs, x >> bws] * inv_area to the
+// upstream gradient as they load it -- no up-sampled gradient image is ever materialised.  W, bh, bw are
+// powers of two here (512 -> 64 is); g == nullptr: no pooled gradient.
+struct PooledGrad {
+    const float* g;   // [B,3,oh,ow]
+    int ws, bhs, bws; // log2(W), log2(bh), log2(bw)
+    int oh, ow;
+    float inv_area;
+};
+inline PooledGrad no_pooled_grad() { return PooledGrad{nullptr, 0, 0, 0, 0, 0, 0.f}; }
+__device__ __forceinline__ float pooled_at(const PooledGrad& pg, int b, int ch, int y, int x) {
+    return __ldg(pg.g + (((size_t)b * 3 + ch) * pg.oh + (y >> pg.bhs)) * pg.ow + (x >> pg.bws)) * pg.inv_area;
+}
+
 // Filter-bank launches (aisp_bank_*): F filters applied to the same batch.  "Virtual sample"
 // v = image * F + slot indexes out / params / grad_out / grad_params / scratch; the image (and the
 // compact NLM stash) is indexed by v / F.  A family's launch only covers its own `n` slots: the

@@ -9,16 +9,16 @@ cudaError_t launch_pointwise_bank_fwd(const float*, float*, const float*, int, i
 cudaError_t launch_pointwise_bank_bwd(const float*, const float*, const float*, int, int, int, int, float*, float*, BankMap,
                                       bool, cudaStream_t);
 cudaError_t launch_pointwise_bwd(const float*, const float*, const float*, const int32_t*, int, int, int, int, float*,
-                                 float*, float*, BankMap, cudaStream_t);
+                                 float*, float*, BankMap, PooledGrad, cudaStream_t);
 cudaError_t launch_sharpen_fwd(const float*, float*, const float*, const int32_t*, int, int, int, BankMap, cudaStream_t);
 cudaError_t launch_sharpen_bwd(const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*,
-                               float*, float*, BankMap, cudaStream_t);
+                               float*, float*, BankMap, PooledGrad, cudaStream_t);
 cudaError_t launch_nlm_fwd(const float*, float*, const float*, const int32_t*, int, int, int, float*, float*, BankMap,
                            cudaStream_t);
 cudaError_t launch_nlm_bwd_img(const float*, const float*, const float*, const float*, const float*, const int32_t*, int,
                                int, int, float*, cudaStream_t);
 cudaError_t launch_nlm_bwd(const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*, BankMap,
-                           cudaStream_t);
+                           PooledGrad, cudaStream_t);
 cudaError_t launch_block_mean(const float*, float*, int, int, int, int, int, cudaStream_t);
 cudaError_t launch_pointwise_chain_bwd(const float*, const float*, const float*, const int32_t*, const int32_t*, int, int,
                                        int, int, int, float*, float*, float*, cudaStream_t);
@@ -102,7 +102,7 @@ int aisp_pointwise_bwd(const float* img, const float* grad_out, const float* par
     if (scratch_bytes < aisp_bwd_scratch_bytes(B, H, W)) return AISP_ERR_SCRATCH;
     if (!al4(img) || !al4(grad_out) || !al4(grad_img)) return AISP_ERR_ALIGN;
     return (int)launch_pointwise_bwd(img, grad_out, params, ops, B, H, W, clip ? 1 : 0, grad_params, grad_img,
-                                     (float*)scratch, plain_batch(), (cudaStream_t)stream);
+                                     (float*)scratch, plain_batch(), no_pooled_grad(), (cudaStream_t)stream);
 }
 
 int aisp_pointwise_chain_bwd(const float* img, const float* grad_out, const float* params, const int32_t* ops,
@@ -133,7 +133,7 @@ int aisp_sharpen_bwd(const float* img, const float* grad_out, const float* param
     if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
     if (scratch_bytes < aisp_bwd_scratch_bytes(B, H, W)) return AISP_ERR_SCRATCH;
     return (int)launch_sharpen_bwd(img, grad_out, params, ops, B, H, W, grad_params, grad_img, gy_scratch,
-                                   (float*)scratch, plain_batch(), (cudaStream_t)stream);
+                                   (float*)scratch, plain_batch(), no_pooled_grad(), (cudaStream_t)stream);
 }
 
 int aisp_nlm_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,
@@ -150,7 +150,7 @@ int aisp_nlm_bwd(const float* grad_out, const float* dout_dh, const int32_t* ops
     if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
     if (scratch_bytes < aisp_bwd_scratch_bytes(B, H, W)) return AISP_ERR_SCRATCH;
     return (int)launch_nlm_bwd(grad_out, dout_dh, nullptr, ops, B, H, W, grad_params, (float*)scratch, plain_batch(),
-                               (cudaStream_t)stream);
+                               no_pooled_grad(), (cudaStream_t)stream);
 }
 
 int aisp_nlm_bwd_img(const float* img, const float* out, const float* wsum, const float* grad_out,
@@ -201,6 +201,47 @@ int aisp_select_apply_bwd(const float* img, const float* out, const float* grad_
     if (e) return e;
     if (grad_img) e = aisp_nlm_bwd_img(img, out, nlm_wsum, grad_out, params, ops, B, H, W, grad_img, stream);
     return e;
+}
+
+// Backward of aisp_sequence_fwd with S == 1 (the select-apply step) when a gradient also reaches the block
+// means: it is added to the upstream gradient inside the kernels' loads (PooledGrad).
+static inline int ilog2_exact(int v) {
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int k = 0;
+    while ((1 << k) < v) ++k;
+    return k;
+}
+
+int aisp_select_apply_bwd_pooled(const float* img, const float* out, const float* grad_out, const float* grad_down,
+                                 int down_h, int down_w, const float* params, const int32_t* ops, int B, int H, int W,
+                                 int clip, const float* nlm_dout_dh, const float* nlm_wsum, float* grad_params,
+                                 float* grad_img, float* gy_scratch, void* scratch, size_t scratch_bytes, void* stream) {
+    if (!img || !grad_out || !grad_down || !params || !ops || !grad_params || !scratch) return AISP_ERR_NULL;
+    if (!shape_ok(B, H, W) || down_h <= 0 || down_w <= 0 || H % down_h || W % down_w) return AISP_ERR_SHAPE;
+    if (scratch_bytes < aisp_bwd_scratch_bytes(B, H, W)) return AISP_ERR_SCRATCH;
+    // the NLM image-gradient kernel (rare path) has no pooled input: parameter gradients only here
+    (void)out; (void)nlm_wsum; (void)gy_scratch;
+    if (grad_img) return AISP_ERR_UNSUPPORTED;
+    PooledGrad pg;
+    pg.g = grad_down;
+    pg.ws = ilog2_exact(W);
+    pg.bhs = ilog2_exact(H / down_h);
+    pg.bws = ilog2_exact(W / down_w);
+    pg.oh = down_h;
+    pg.ow = down_w;
+    pg.inv_area = 1.0f / (float)((H / down_h) * (W / down_w));
+    // (a pooling block must not split a 4-pixel vector: block width >= 4 or the scalar path)
+    if (pg.ws < 0 || pg.bhs < 0 || pg.bws < 0 || ((W / down_w) < 4 && (W % 4) == 0)) return AISP_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = launch_pointwise_bwd(img, grad_out, params, ops, B, H, W, clip ? 1 : 0, grad_params, nullptr,
+                                         (float*)scratch, plain_batch(), pg, st);
+    if (e != cudaSuccess) return (int)e;
+    e = launch_sharpen_bwd(img, grad_out, params, ops, B, H, W, grad_params, nullptr, nullptr, (float*)scratch,
+                           plain_batch(), pg, st);
+    if (e != cudaSuccess) return (int)e;
+    if (nlm_dout_dh)
+        e = launch_nlm_bwd(grad_out, nlm_dout_dh, nullptr, ops, B, H, W, grad_params, (float*)scratch, plain_batch(), pg, st);
+    return (int)e;
 }
 
 int aisp_select(const float* pdf, const float* noise, int mode, int forced_id, const float* states,
@@ -354,10 +395,10 @@ int aisp_bank_bwd(const float* img, const float* grad_out, const float* params, 
                                       true, st);
     if (e == cudaSuccess && m[FAMILY_SHARPEN].n)
         e = launch_sharpen_bwd(img, grad_out, params, nullptr, B * m[FAMILY_SHARPEN].n, H, W, grad_params, nullptr,
-                               nullptr, (float*)scratch, m[FAMILY_SHARPEN], st);
+                               nullptr, (float*)scratch, m[FAMILY_SHARPEN], no_pooled_grad(), st);
     if (e == cudaSuccess && m[FAMILY_NLM].n && nlm_dout_dh)
         e = launch_nlm_bwd(grad_out, nlm_dout_dh, nullptr, nullptr, B * m[FAMILY_NLM].n, H, W, grad_params,
-                           (float*)scratch, m[FAMILY_NLM], st);
+                           (float*)scratch, m[FAMILY_NLM], no_pooled_grad(), st);
     return (int)e;
 }
 

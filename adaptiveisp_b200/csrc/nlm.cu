@@ -321,7 +321,7 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
 // grad_h[b] = sum g * dout_dh : plain streaming dot product, chunked like the per-pixel kernels
 __global__ void __launch_bounds__(kThreads)
 nlm_dot_kernel(const float* __restrict__ gout, const float* __restrict__ stash, const int32_t* __restrict__ ops,
-               long long n /* 3*H*W */, float* __restrict__ partial, BankMap bm) {
+               long long n /* 3*H*W */, float* __restrict__ partial, BankMap bm, PooledGrad pool) {
     pdl_prologue();
     __shared__ float red[kWarps * AISP_ACC_STRIDE];
     const int b = bank_sample(bm, blockIdx.y);
@@ -331,13 +331,26 @@ nlm_dot_kernel(const float* __restrict__ gout, const float* __restrict__ stash, 
     float acc[1] = {0.f};
     const long long lo = (long long)blockIdx.x * (3 * kPwChunkPx);
     const long long hi = min(lo + 3 * kPwChunkPx, n);
+    const long long plane = n / 3;
+    // the gradient of the pooled image at flat element i of the [3,H,W] sample
+    auto pooled = [&](long long i) {
+        const int ch = (i >= 2 * plane) ? 2 : (i >= plane ? 1 : 0);
+        const int rem = (int)(i - ch * plane);
+        return pooled_at(pool, b, ch, rem >> pool.ws, rem & ((1 << pool.ws) - 1));
+    };
     if (((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(stash)) & 15u) == 0) {
         for (long long i = lo + 4 * threadIdx.x; i < hi; i += 4 * kThreads) {
-            const float4 a = ldg_stream4(g + i), c = ldg_stream4(s + i);
+            float4 a = ldg_stream4(g + i);
+            const float4 c = ldg_stream4(s + i);
+            if (pool.g) {   // (W % 4 == 0 here: the four elements share a row and a pooling block)
+                const float u = pooled(i);
+                a.x += u; a.y += u; a.z += u; a.w += u;
+            }
             acc[0] += (a.x * c.x + a.y * c.y) + (a.z * c.z + a.w * c.w);
         }
     } else {
-        for (long long i = lo + threadIdx.x; i < hi; i += kThreads) acc[0] = fmaf(g[i], s[i], acc[0]);
+        for (long long i = lo + threadIdx.x; i < hi; i += kThreads)
+            acc[0] = fmaf(pool.g ? g[i] + pooled(i) : g[i], s[i], acc[0]);
     }
     block_reduce_store<1>(acc, red, partial + ((size_t)b * gridDim.x + blockIdx.x) * AISP_ACC_STRIDE);
 }
@@ -519,11 +532,12 @@ cudaError_t launch_nlm_bwd_img(const float* img, const float* out, const float* 
 }
 
 cudaError_t launch_nlm_bwd(const float* gout, const float* stash, const float* params_unused, const int32_t* ops,
-                           int B, int H, int W, float* grad_params, float* partial, BankMap bm, cudaStream_t st) {
+                           int B, int H, int W, float* grad_params, float* partial, BankMap bm, PooledGrad pool,
+                           cudaStream_t st) {
     (void)params_unused;
     const int rows = pointwise_rows(H, W);
     dim3 grid(rows, B);
-    launch_pdl(nlm_dot_kernel, grid, kThreads, st, gout, stash, ops, 3LL * H * W, partial, bm);
+    launch_pdl(nlm_dot_kernel, grid, kThreads, st, gout, stash, ops, 3LL * H * W, partial, bm, pool);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // finalize reads params only to derive constants; NLM needs none, so grad_params doubles as a

@@ -239,7 +239,7 @@ pw_bank_fwd_kernel(const float* __restrict__ img, float* __restrict__ out, const
 template <int OP, int VEC, bool GIMG, bool CLIP>
 __device__ __forceinline__ void pw_bwd_body(const float* __restrict__ pr, const float* __restrict__ pg,
                                             float* __restrict__ gi, const float* c, int N, int chunk,
-                                            float* red, float* dst) {
+                                            float* red, float* dst, const PooledGrad& pool, int b) {
     constexpr int NACC = PwBwd<OP>::NACC;
     constexpr int GROUPS = kPwChunkPx / (kThreads * VEC);
     constexpr int G = (VEC == 4) ? 1 : 4;  // 4 px per thread per round (6 LDG.128 in flight), 3 CTAs/SM
@@ -255,6 +255,13 @@ __device__ __forceinline__ void pw_bwd_body(const float* __restrict__ pr, const 
             if (i < N) {
                 xr[j].load(pr + i); xg[j].load(pr + N + i); xb[j].load(pr + 2 * (size_t)N + i);
                 dr[j].load(pg + i); dg[j].load(pg + N + i); db[j].load(pg + 2 * (size_t)N + i);
+                if (pool.g) {   // + the gradient of the pooled image (the VEC pixels share one pooling block)
+                    const int y = i >> pool.ws, x = i & ((1 << pool.ws) - 1);
+                    const float ar = pooled_at(pool, b, 0, y, x), ag = pooled_at(pool, b, 1, y, x),
+                                ab = pooled_at(pool, b, 2, y, x);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) { dr[j].v[v] += ar; dg[j].v[v] += ag; db[j].v[v] += ab; }
+                }
             } else {
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
@@ -289,7 +296,7 @@ template <int VEC, bool GIMG, bool COLOR>
 __global__ void __launch_bounds__(kThreads, COLOR ? 1 : 4)
 pw_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, const float* __restrict__ params,
               const int32_t* __restrict__ ops, int N, int clip, int nchunks, float* __restrict__ gimg,
-              float* __restrict__ partial, BankMap bm) {
+              float* __restrict__ partial, BankMap bm, PooledGrad pool) {
     pdl_prologue();
     __shared__ float raw[1][kConst];
     __shared__ float sc[1][kConst];
@@ -322,8 +329,8 @@ pw_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, con
         // the clip flag is CTA-uniform: one branch here instead of a predicate on every pixel
 #define AISP_CASE(OPC)                                                                     \
     case OPC:                                                                              \
-        if (clip) pw_bwd_body<OPC, VEC, GIMG, true>(pr, pg, gi, c, N, chunk, red, dst);    \
-        else pw_bwd_body<OPC, VEC, GIMG, false>(pr, pg, gi, c, N, chunk, red, dst);        \
+        if (clip) pw_bwd_body<OPC, VEC, GIMG, true>(pr, pg, gi, c, N, chunk, red, dst, pool, b);    \
+        else pw_bwd_body<OPC, VEC, GIMG, false>(pr, pg, gi, c, N, chunk, red, dst, pool, b);        \
         break;
         if (COLOR) {
             switch (op) {
@@ -600,7 +607,7 @@ cudaError_t launch_finalize(const float* partial, int nrows, const float* params
 
 cudaError_t launch_pointwise_bwd(const float* img, const float* gout, const float* params, const int32_t* ops,
                                  int B, int H, int W, int clip, float* grad_params, float* grad_img,
-                                 float* partial, BankMap bm, cudaStream_t st) {
+                                 float* partial, BankMap bm, PooledGrad pool, cudaStream_t st) {
     const long long N = (long long)H * W;
     const int rows = pointwise_rows(H, W);
     // main launch: CTA <-> (sample, chunk); ColorFilter launch: one CTA per sample (see pw_bwd_kernel)
@@ -609,9 +616,9 @@ cudaError_t launch_pointwise_bwd(const float* img, const float* gout, const floa
 #define AISP_LAUNCH(VEC, GIMG)                                                                                        \
     do {                                                                                                              \
         launch_pdl(pw_bwd_kernel<VEC, GIMG, false>, grid, kThreads, st, img, gout, params, ops, (int)N, clip, rows,  \
-                   grad_img, partial, bm);                                                                            \
+                   grad_img, partial, bm, pool);                                                                      \
         launch_pdl(pw_bwd_kernel<VEC, GIMG, true>, grid_color, kThreads, st, img, gout, params, ops, (int)N, clip,   \
-                   rows, grad_img, partial, bm);                                                                      \
+                   rows, grad_img, partial, bm, pool);                                                                \
     } while (0)
     if (vec) {
         if (grad_img) AISP_LAUNCH(4, true);

@@ -192,7 +192,8 @@ template <bool BWD, bool WRITE_GY>
 __global__ void __launch_bounds__(kThreads, BWD ? 3 : 4)
 sharpen_kernel(const __grid_constant__ CUtensorMap tmap, int tma_ok, const float* __restrict__ img,
                const float* __restrict__ gout, float* __restrict__ out, const float* __restrict__ params,
-               const int32_t* __restrict__ ops, int H, int W, int vec, float* __restrict__ partial, BankMap bm) {
+               const int32_t* __restrict__ ops, int H, int W, int vec, float* __restrict__ partial, BankMap bm,
+               PooledGrad pool) {
     pdl_prologue();
     __shared__ __align__(128) float sm[kSmFloats];
     __shared__ __align__(8) unsigned long long bar;
@@ -255,6 +256,11 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, int tma_ok, const float
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         gpre[ch][r][i] = (gy < H && gx0 + i < W) ? gout[off + i] : 0.f;
+                }
+                if (pool.g && gy < H) {   // + the gradient of the pooled image
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (gx0 + i < W) gpre[ch][r][i] += pooled_at(pool, b, ch, gy, gx0 + i);
                 }
             }
     }
@@ -628,7 +634,7 @@ cudaError_t launch_sharpen_fwd(const float* img, float* out, const float* params
     CUtensorMap map;
     const int tma_ok = make_tile_map(&map, img, bm.n ? B / bm.n : B, H, W) ? 1 : 0;
     launch_pdl(sharpen_kernel<false, false>, grid, kThreads, st, map, tma_ok, img, nullptr, out, params, ops, H, W, vec,
-               nullptr, bm);
+               nullptr, bm, no_pooled_grad());
     return cudaGetLastError();
 }
 
@@ -672,17 +678,17 @@ cudaError_t launch_sharpen_seq_fwd(const float* img, float* out, const float* pa
 
 cudaError_t launch_sharpen_bwd(const float* img, const float* gout, const float* params, const int32_t* ops, int B,
                                int H, int W, float* grad_params, float* grad_img, float* gy_scratch, float* partial,
-                               BankMap bm, cudaStream_t st) {
+                               BankMap bm, PooledGrad pool, cudaStream_t st) {
     dim3 grid((W + kShTileW - 1) / kShTileW, (H + kShTileH - 1) / kShTileH, B);
     const int vec = ((W & 3) == 0) && al16(img) && al16(gout) && (!grad_img || al16(gy_scratch));
     CUtensorMap map;
     const int tma_ok = make_tile_map(&map, img, bm.n ? B / bm.n : B, H, W) ? 1 : 0;
     if (grad_img)
         launch_pdl(sharpen_kernel<true, true>, grid, kThreads, st, map, tma_ok, img, gout, gy_scratch, params, ops, H, W, vec,
-                   partial, bm);
+                   partial, bm, pool);
     else
         launch_pdl(sharpen_kernel<true, false>, grid, kThreads, st, map, tma_ok, img, gout, nullptr, params, ops, H, W, vec,
-                   partial, bm);
+                   partial, bm, pool);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     e = launch_finalize(partial, sharpen_rows(H, W), params, ops, FAMILY_SHARPEN, B, grad_params, bm, st);

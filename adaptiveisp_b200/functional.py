@@ -124,8 +124,24 @@ class _ApplyOps(torch.autograd.Function):
         if not (need_img or need_p) or (g is None and g_down is None):
             return None, None, None, None, None, None, None
         if g_down is not None:
-            # d(block mean)/d(pixel) = 1 / (bh * bw): spread the pooled gradient over its block
+            g_down = g_down.contiguous()
             bh, bw = H // g_down.shape[2], W // g_down.shape[3]
+            pow2 = all(v > 0 and (v & (v - 1)) == 0 for v in (W, bh, bw)) and (bw >= 4 or W % 4 != 0)
+            if pow2 and not need_img and ctx.family == FAMILY_MIXED and g_down.dtype == torch.float32:
+                # the pooled gradient is added inside the backward kernels' loads (aisp_select_apply_bwd_pooled)
+                if g is None:
+                    g = torch.zeros_like(img)
+                g = g.contiguous()
+                gP = torch.zeros_like(P)
+                sc = _lib.scratch(B, H, W, img.device)
+                with torch.cuda.device(img.device):
+                    rc = _lib.lib().aisp_select_apply_bwd_pooled(
+                        img.data_ptr(), None, g.data_ptr(), g_down.data_ptr(), g_down.shape[2], g_down.shape[3],
+                        P.data_ptr(), ops.data_ptr(), B, H, W, int(ctx.clip), _lib.ptr(stash), None, gP.data_ptr(), None,
+                        None, sc.data_ptr(), sc.numel(), _lib.stream_ptr(img.device))
+                _lib.check(rc, "aisp_select_apply_bwd_pooled")
+                return None, (gP if need_p else None), None, None, None, None, None
+            # otherwise: d(block mean)/d(pixel) = 1 / (bh * bw), spread the pooled gradient over its block
             up = (g_down * (1.0 / (bh * bw))).repeat_interleave(bh, dim=2).repeat_interleave(bw, dim=3)
             g = up if g is None else g + up
         g = g.contiguous()

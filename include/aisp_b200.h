@@ -235,6 +235,19 @@ int aisp_sequence_fwd(const float* img, float* out, const float* params, const i
                       float* down, int down_h, int down_w, float* nlm_dout_dh, float* nlm_wsum, void* stream);
 
 /*
+ * aisp_select_apply_bwd when a gradient ALSO reaches the block means of the output (aisp_sequence_fwd's
+ * `down`: the critic pools the retouched image, value.py:63, so train.py:341-342 differentiates through the
+ * pooled image too).  grad_down [B,3,down_h,down_w] is added, divided by the block area, to grad_out inside
+ * the kernels' loads: no up-sampled gradient image is materialised.  Parameter gradients only (grad_img
+ * must be NULL); W and the pooling block sides must be powers of two (512 -> 64 is), else
+ * AISP_ERR_UNSUPPORTED and the caller adds the up-sampled gradient itself.
+ */
+int aisp_select_apply_bwd_pooled(const float* img, const float* out, const float* grad_out, const float* grad_down,
+                                 int down_h, int down_w, const float* params, const int32_t* ops, int B, int H, int W,
+                                 int clip, const float* nlm_dout_dh, const float* nlm_wsum, float* grad_params,
+                                 float* grad_img, float* gy_scratch, void* scratch, size_t scratch_bytes, void* stream);
+
+/*
  * Device-side filter selection + agent-state update in one launch, no host round trip:
  * pdf_sample / argmax / forced id (agent.py:12-16,126-149), one_hot (agent.py:18-23), the gather
  * of the selected filter's parameter row (the B200 form of agent.py:154: pick the row before the
