@@ -603,31 +603,38 @@ def test_block_means_leave_through_the_store_path(dev, size, out):
     assert float(down[3].abs().max()) == 0.0                         # AISP_OP_NONE: zero image, zero means
 
 
-def test_gradient_through_emitted_block_means(dev):
+@pytest.mark.parametrize("H,W,out", [(128, 128, (16, 16)), (96, 160, (32, 32)), (64, 256, (16, 128))])
+def test_gradient_through_emitted_block_means(dev, H, W, out):
     """train.py:283: the critic pools the RETOUCHED image (value.py:63), so a gradient reaches the block
-    means; it must act on the filter parameters exactly as if the image had been pooled by PyTorch."""
+    means; it must act on the filter parameters exactly as if the image had been pooled by PyTorch.
+    (128 -> 16: power-of-two blocks, the pooled gradient is added inside the backward kernels' loads;
+    96x160 -> 32x32: 3x5 blocks, the up-sampled gradient is added up front; 64x256 -> 16x128: 4x2 blocks.)"""
     from adaptiveisp_b200 import functional as AF
-    ops = [O.OP_EXPOSURE, O.OP_TONE, O.OP_SHARPEN, O.OP_NLM, O.OP_CCM]
-    B, H, W = len(ops), 128, 128
+    ops = [O.OP_EXPOSURE, O.OP_TONE, O.OP_SHARPEN, O.OP_NLM, O.OP_CCM, O.OP_USM, O.OP_SATPLUS]
+    B = len(ops)
     img = cases.lod_batch(B, H, W, seed=51, device=dev)
     P0 = torch.cat([AF.pack_params(cases.params_for(op, 1, seed=60 + b)[1], O.OP_NPARAMS[op]) for b, op in enumerate(ops)], 0)
     ops_t = torch.tensor(ops, dtype=torch.int32, device=dev)
     g = cases.grad_out((B, 3, H, W), 5).to(dev)
-    gd = cases.grad_out((B, 3, 16, 16), 6).to(dev).abs()
+    gd = cases.grad_out((B, 3) + tuple(out), 6).to(dev).abs() * 40.0      # comparable in size to the direct gradient
     Pa = P0.to(dev).requires_grad_(True)
-    y, _, down = AF.apply_ops(img, Pa, ops_t, clip=True, down_hw=(16, 16))
+    y, _, down = AF.apply_ops(img, Pa, ops_t, clip=True, down_hw=out)
     ((y * g).sum() + (down * gd).sum()).backward()
     Pb = P0.to(dev).requires_grad_(True)
     y2 = AF.apply_ops(img, Pb, ops_t, clip=True)
-    ((y2 * g).sum() + (torch.nn.AdaptiveAvgPool2d((16, 16))(y2) * gd).sum()).backward()
+    ((y2 * g).sum() + (torch.nn.AdaptiveAvgPool2d(out)(y2) * gd).sum()).backward()
     for b, op in enumerate(ops):
         n = O.OP_NPARAMS[op]
         assert_grad(Pa.grad[b, :n].cpu().numpy(), Pb.grad[b, :n].cpu().numpy(), 2e-5, O.OP_NAMES[op])
     # only the pooled image is used: the full-resolution gradient is absent altogether
     Pc = P0.to(dev).requires_grad_(True)
-    _, _, d3 = AF.apply_ops(img, Pc, ops_t, clip=True, down_hw=(16, 16))
+    _, _, d3 = AF.apply_ops(img, Pc, ops_t, clip=True, down_hw=out)
     (d3 * gd).sum().backward()
-    assert bool(torch.isfinite(Pc.grad).all()) and float(Pc.grad.abs().max()) > 0
+    Pd = P0.to(dev).requires_grad_(True)
+    (torch.nn.AdaptiveAvgPool2d(out)(AF.apply_ops(img, Pd, ops_t, clip=True)) * gd).sum().backward()
+    for b, op in enumerate(ops):
+        n = O.OP_NPARAMS[op]
+        assert_grad(Pc.grad[b, :n].cpu().numpy(), Pd.grad[b, :n].cpu().numpy(), 5e-5, "pooled only " + O.OP_NAMES[op])
 
 
 def test_agent_output_carries_block_means_for_the_critic(dev):
