@@ -36,6 +36,7 @@ cudaError_t launch_block_mean_masked(const float*, float*, int, int, int, int, i
 cudaError_t launch_regress(const float*, const int32_t*, const int32_t*, int, int, int, const float*, float*, const float*,
                            float*, cudaStream_t);
 cudaError_t launch_value_stats(const float*, int, int, float*, cudaStream_t);
+cudaError_t launch_nlm_module_fwd(const float*, float*, const float*, const int32_t*, int, int, int, float*, int, cudaStream_t);
 bool pointwise_can_emit(int, int, int, int);
 bool sharpen_can_emit(int, int, int, int);
 int chain_bwd_max_steps();
@@ -142,6 +143,14 @@ int aisp_nlm_fwd(const float* img, float* out, const float* params, const int32_
     if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
     if (img == out) return AISP_ERR_UNSUPPORTED;
     return (int)launch_nlm_fwd(img, out, params, ops, B, H, W, dout_dh, wsum, plain_batch(), (cudaStream_t)stream);
+}
+
+int aisp_nlm_module_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,
+                        float* dout_dh, int gray, void* stream) {
+    if (!img || !out || !params || !ops) return AISP_ERR_NULL;
+    if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
+    if (img == out) return AISP_ERR_UNSUPPORTED;
+    return (int)launch_nlm_module_fwd(img, out, params, ops, B, H, W, dout_dh, gray ? 1 : 0, (cudaStream_t)stream);
 }
 
 int aisp_nlm_bwd(const float* grad_out, const float* dout_dh, const int32_t* ops, int B, int H, int W,

@@ -81,6 +81,12 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
     return r;
 }
 
+// variant: 0 = DenoiseFilter.process (isp/filters.py:582-586: input clipped, gray distance);
+//   1 = the bare NonLocalMeansGray module (isp/denoise.py:93-119): distances on the luma of the CLIPPED
+//       image (rgb_to_luminance clips, :14), averages of the UNclipped one;
+//   2 + c = channel c of the bare NonLocalMeans module (isp/denoise.py:68-90): per-channel distances and
+//       weights on the unclipped image -- the host runs c = 0, 1, 2 (each pass writes its own channel).
+//   Variants >= 1 are modules, not Filters: no lerp term.
 // SEQ: the sample's op SEQUENCE [per-pixel prologue] -> NLM -> [per-pixel epilogue] in one launch (params
 // [B,S,PSTRIDE], ops [B,S]): the prologue runs on every pixel as it is staged (tile + halo, wrapped
 // circularly: per-pixel filters commute with the wrap), the epilogue on the finished outputs in
@@ -89,7 +95,7 @@ template <bool WITH_GRAD, int LW, bool SEQ>
 __global__ void __launch_bounds__(kThreads, WITH_GRAD ? 3 : 4)
 nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __restrict__ dout_dh,
            float* __restrict__ wsum_out, const float* __restrict__ params, const int32_t* __restrict__ ops, int H,
-           int W, int x_off, BankMap bm, const int32_t* __restrict__ seq_len, int S, int clip_each) {
+           int W, int x_off, BankMap bm, const int32_t* __restrict__ seq_len, int S, int clip_each, int variant) {
     pdl_prologue();
     using Geo = NlmGeo<LW>;
     constexpr int kNlmSmH = Geo::SH, kNlmSmW = Geo::SW;
@@ -154,13 +160,16 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
                     if (clip_each) { r = clip01(r); g = clip01(g); bl = clip01(bl); }
                 }
             }
-            r = clip01(r); g = clip01(g); bl = clip01(bl);
+            const float cr = clip01(r), cg = clip01(g), cb = clip01(bl);
+            float yy = (0.299f * cr + 0.587f * cg) + 0.114f * cb;
+            if (variant == 0) { r = cr; g = cg; bl = cb; }                       // the filter averages what it clipped
+            else if (variant >= 2) yy = (variant == 2) ? r : (variant == 3 ? g : bl);
             const bool in = e < kStageN;
             if (in) {
                 sC[0][row][col] = r;
                 sC[1][row][col] = g;
                 sC[2][row][col] = bl;
-                sY[row][col] = (0.299f * r + 0.587f * g) + 0.114f * bl;
+                sY[row][col] = yy;
             }
             // "this staged row holds a non-zero value" (NaN counts): the lanes of a warp that staged the same
             // row vote, the lowest of them ORs the flag in (a warp's 32 consecutive elements span 2-3 rows)
@@ -299,11 +308,14 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
             // 0 * x: the (1 - mask) * img term of the reference's lerp (isp/filters.py:115), NaN iff the
             // filter's input pixel is inf / NaN.  Plain kernel: the UNclipped centre pixel (an L2 hit, the
             // tile was just staged); after a fused prologue the staged (clipped) value stands in for it.
-            const float xin = (SEQ && pos > 0) ? sC[c][r0 + i + kNlmHalo][lane + kNlmHalo]
-                                               : __ldg(src + (size_t)c * plane + (size_t)gy * W + gx);
-            const float y = fmaf(0.f, xin, ac[c][i] * iw);
+            float y = ac[c][i] * iw;
+            if (variant == 0) {
+                const float xin = (SEQ && pos > 0) ? sC[c][r0 + i + kNlmHalo][lane + kNlmHalo]
+                                                   : __ldg(src + (size_t)c * plane + (size_t)gy * W + gx);
+                y = fmaf(0.f, xin, y);
+            }
             yv[c] = clip01(y);
-            if (WITH_GRAD)
+            if (WITH_GRAD && (variant < 2 || c == variant - 2))
                 dout_dh[sb * 3 * plane + (size_t)c * plane + (size_t)gy * W + gx] =
                     pass01(y) * (bc[c][i] - y * wd[i]) * iw * inv_h2;
         }
@@ -314,7 +326,8 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
             }
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) out[(size_t)b * 3 * plane + (size_t)c * plane + (size_t)gy * W + gx] = yv[c];
+        for (int c = 0; c < 3; ++c)
+            if (variant < 2 || c == variant - 2) out[(size_t)b * 3 * plane + (size_t)c * plane + (size_t)gy * W + gx] = yv[c];
     }
 }
 
@@ -363,7 +376,7 @@ int pointwise_rows(int H, int W);
 // (12 columns x 64 rows per CTA).  seq == true: per-sample sequences (see nlm_kernel<.., SEQ>).
 static cudaError_t launch_nlm_any(const float* img, float* out, const float* params, const int32_t* ops, int B, int H,
                                   int W, float* dout_dh, float* wsum, BankMap bm, bool seq, const int32_t* seq_len,
-                                  int S, int clip_each, cudaStream_t st) {
+                                  int S, int clip_each, int variant, cudaStream_t st) {
     using G32 = NlmGeo<32>;
     using G16 = NlmGeo<16>;
     int n32 = W / G32::TW;
@@ -374,39 +387,51 @@ static cudaError_t launch_nlm_any(const float* img, float* out, const float* par
         dim3 grid(n32, (H + G32::TH - 1) / G32::TH, B);
         if (seq)
             launch_pdl(nlm_kernel<false, 32, true>, grid, kThreads, st, img, out, nullptr, nullptr, params, ops, H, W, 0, bm,
-                       seq_len, S, clip_each);
+                       seq_len, S, clip_each, variant);
         else if (dout_dh)
             launch_pdl(nlm_kernel<true, 32, false>, grid, kThreads, st, img, out, dout_dh, wsum, params, ops, H, W, 0, bm,
-                       nullptr, 1, 0);
+                       nullptr, 1, 0, variant);
         else
             launch_pdl(nlm_kernel<false, 32, false>, grid, kThreads, st, img, out, nullptr, wsum, params, ops, H, W, 0, bm,
-                       nullptr, 1, 0);
+                       nullptr, 1, 0, variant);
     }
     if (half) {
         dim3 grid(1, (H + G16::TH - 1) / G16::TH, B);
         const int x_off = n32 * G32::TW;
         if (seq)
             launch_pdl(nlm_kernel<false, 16, true>, grid, kThreads, st, img, out, nullptr, nullptr, params, ops, H, W, x_off,
-                       bm, seq_len, S, clip_each);
+                       bm, seq_len, S, clip_each, variant);
         else if (dout_dh)
             launch_pdl(nlm_kernel<true, 16, false>, grid, kThreads, st, img, out, dout_dh, wsum, params, ops, H, W, x_off, bm,
-                       nullptr, 1, 0);
+                       nullptr, 1, 0, variant);
         else
             launch_pdl(nlm_kernel<false, 16, false>, grid, kThreads, st, img, out, nullptr, wsum, params, ops, H, W, x_off,
-                       bm, nullptr, 1, 0);
+                       bm, nullptr, 1, 0, variant);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_nlm_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,
                            float* dout_dh, float* wsum, BankMap bm, cudaStream_t st) {
-    return launch_nlm_any(img, out, params, ops, B, H, W, dout_dh, wsum, bm, false, nullptr, 1, 0, st);
+    return launch_nlm_any(img, out, params, ops, B, H, W, dout_dh, wsum, bm, false, nullptr, 1, 0, 0, st);
+}
+
+// the bare modules of isp/denoise.py (see `variant` at nlm_kernel): gray = NonLocalMeansGray, else NonLocalMeans
+cudaError_t launch_nlm_module_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H,
+                                  int W, float* dout_dh, int gray, cudaStream_t st) {
+    if (gray) return launch_nlm_any(img, out, params, ops, B, H, W, dout_dh, nullptr, plain_batch(), false, nullptr, 1, 0, 1, st);
+    for (int c = 0; c < 3; ++c) {
+        cudaError_t e = launch_nlm_any(img, out, params, ops, B, H, W, dout_dh, nullptr, plain_batch(), false, nullptr, 1,
+                                       0, 2 + c, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 // per-sample sequences [prologue] -> NLM -> [epilogue] (no stashes: S > 1 has no closed-form d/dh)
 cudaError_t launch_nlm_seq_fwd(const float* img, float* out, const float* params, const int32_t* ops,
                                const int32_t* seq_len, int B, int H, int W, int S, int clip_each, cudaStream_t st) {
-    return launch_nlm_any(img, out, params, ops, B, H, W, nullptr, nullptr, plain_batch(), true, seq_len, S, clip_each, st);
+    return launch_nlm_any(img, out, params, ops, B, H, W, nullptr, nullptr, plain_batch(), true, seq_len, S, clip_each, 0, st);
 }
 
 // ---------------------------------------------------------------------------------------------

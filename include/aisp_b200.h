@@ -165,6 +165,19 @@ int aisp_sharpen_bwd(const float* img, const float* grad_out, const float* param
 int aisp_nlm_fwd(const float* img, float* out, const float* params, const int32_t* ops,
                  int B, int H, int W, float* dout_dh, float* wsum, void* stream);
 
+/*
+ * The bare non-local-means MODULES of isp/denoise.py (11x11 search, 5x5 patch), i.e. without the
+ * DenoiseFilter wrapper (no clip of the input, no lerp term):
+ *   gray != 0: NonLocalMeansGray.forward(rgb, h) :93-119 -- distances on the luma of the clipped image
+ *              (rgb_to_luminance clips, :14), averages of the image as given;
+ *   gray == 0: NonLocalMeans.forward(rgb, h) :68-90 -- per-channel distances and weights [B,3,H,W]
+ *              (three passes of the same kernel, one per channel).
+ * params[b,0] = h; ops[b] must be AISP_OP_NLM.  dout_dh as in aisp_nlm_fwd (aisp_nlm_bwd is its backward).
+ * No image gradient for the modules (AispError in the Python layer).
+ */
+int aisp_nlm_module_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,
+                        float* dout_dh, int gray, void* stream);
+
 /* Backward of NLM w.r.t. h:  grad_params[b,0] = sum_{c,y,x} grad_out * dout_dh. */
 int aisp_nlm_bwd(const float* grad_out, const float* dout_dh, const int32_t* ops, int B, int H, int W,
                  float* grad_params, void* scratch, size_t scratch_bytes, void* stream);

@@ -340,6 +340,41 @@ def nlm_gray(img, p, search: int = 11, patch: int = 5):
     return torch.clamp(acc / wsum, 0.0, 1.0)
 
 
+def nlm_gray_module(rgb, h, search: int = 11, patch: int = 5):
+    """The bare ``NonLocalMeansGray(search, patch).forward(rgb, h)`` of isp/denoise.py:93-119 (no filter
+    wrapper): distances on the luma of the CLIPPED image (``rgb_to_luminance`` clips, :14), averages of
+    the image as given.  h broadcastable to ``[B,1,1,1]``."""
+    r = search // 2
+    wsum = torch.zeros((rgb.shape[0], 1, rgb.shape[2], rgb.shape[3]), dtype=rgb.dtype).to(rgb.device)
+    acc = torch.zeros_like(rgb)
+    y = lum_nlm(torch.clip(rgb, 0.0, 1.0))
+    for xs in range(-r, r + 1):
+        for ys in range(-r, r + 1):
+            rgb_s = torch.roll(rgb, shifts=(ys, xs), dims=(2, 3))
+            y_s = torch.roll(y, shifts=(ys, xs), dims=(2, 3))
+            dist = torch.sqrt(torch.relu(_box_sum((y - y_s) ** 2, patch // 2)))
+            w = torch.exp(-dist / (torch.relu(h) + 1e-8))
+            acc += rgb_s * w
+            wsum += w
+    return torch.clamp(acc / wsum, 0.0, 1.0)
+
+
+def nlm_rgb_module(rgb, h, search: int = 11, patch: int = 5):
+    """The bare ``NonLocalMeans(search, patch).forward(rgb, h)`` of isp/denoise.py:68-90: per-channel
+    patch distances and weights ``[B,3,H,W]`` on the image as given (no clip of the input)."""
+    r = search // 2
+    wsum = torch.zeros_like(rgb)
+    acc = torch.zeros_like(rgb)
+    for xs in range(-r, r + 1):
+        for ys in range(-r, r + 1):
+            rgb_s = torch.roll(rgb, shifts=(ys, xs), dims=(2, 3))
+            dist = torch.sqrt(torch.relu(_box_sum((rgb - rgb_s) ** 2, patch // 2)))
+            w = torch.exp(-dist / (torch.relu(h) + 1e-8))
+            acc += rgb_s * w
+            wsum += w
+    return torch.clamp(acc / wsum, 0.0, 1.0)
+
+
 # ----------------------------------------------------------------------------------------------
 # dispatch + Filter.forward / Filter.run wrappers
 # ----------------------------------------------------------------------------------------------

@@ -193,6 +193,24 @@ def agent_golden(ref):
     return out
 
 
+def denoise_modules_golden(ref):
+    """The bare NLM modules of isp/denoise.py: NonLocalMeansGray and NonLocalMeans
+    (per-channel distances) with search 11 / patch 5, on images that spill outside [0,1] (the modules do not
+    clip their input), with the gradient w.r.t. h under a one-signed upstream gradient."""
+    out = {}
+    for name, cls in (("gray", ref.denoise.NonLocalMeansGray), ("rgb", ref.denoise.NonLocalMeans)):
+        for variant, (B, H, W, seed) in {"a": (3, 20, 24, 40), "b": (2, 33, 47, 41)}.items():
+            img = cases.edge_image(B, H, W, seed)                    # samples >= 2 spill outside [0,1]
+            h = (0.15 + 0.5 * torch.rand((B, 1, 1, 1), generator=torch.Generator().manual_seed(seed))).requires_grad_(True)
+            g = cases.grad_out(img.shape, seed).abs()
+            y = cls(search_window_size=11, patch_size=5)(img, h)
+            (y * g).sum().backward()
+            key = f"{name}.{variant}"
+            out[key + ".img"], out[key + ".h"], out[key + ".g"] = img.numpy(), h.detach().numpy(), g.numpy()
+            out[key + ".out"], out[key + ".gh"] = y.detach().numpy(), h.grad.numpy()
+    return out
+
+
 def main():
     ref = ref_shim.load()
     a = agent_golden(ref)
@@ -202,6 +220,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "filters.npz"), **f)
     s = select_golden(ref)
     np.savez_compressed(os.path.join(HERE, "select.npz"), **s)
+    d = denoise_modules_golden(ref)
+    np.savez_compressed(os.path.join(HERE, "denoise_modules.npz"), **d)
     for fn in ("filters.npz", "select.npz"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")
 

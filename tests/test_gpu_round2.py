@@ -776,3 +776,49 @@ def test_value_statistics_kernel_matches_the_pytorch_statement(dev):
         err = ((got - ref).abs() / ref.abs().clamp_min(1e-3)).max()
         assert float(err) <= 1e-5, (B, h, w, got, ref)
         assert float(((got - ref32).abs() / ref32.abs().clamp_min(1e-3)).max()) <= 1e-4
+
+
+# ----------------------------------------------------------------------------------------------
+# 10. the bare NLM modules of isp/denoise.py (rows A11 / A12): NonLocalMeansGray and NonLocalMeans (RGB)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["gray", "rgb"])
+@pytest.mark.parametrize("variant", ["a", "b"])
+def test_bare_nlm_modules_match_reference_vectors(dev, name, variant):
+    """adaptiveisp_b200.denoise.NonLocalMeansGray / NonLocalMeans (per-channel distances and weights) against
+    vectors from the unmodified reference: images that spill outside [0,1] (the modules do not clip their
+    input: the gray variant measures distances on the clipped luma but averages the raw image), outputs and
+    the gradient w.r.t. h."""
+    import os
+    from adaptiveisp_b200 import denoise as D
+    G = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "denoise_modules.npz")))
+    key = f"{name}.{variant}"
+    img, g = torch.from_numpy(G[key + ".img"]).to(dev), torch.from_numpy(G[key + ".g"]).to(dev)
+    h = torch.from_numpy(G[key + ".h"]).to(dev).requires_grad_(True)
+    mod = (D.NonLocalMeansGray if name == "gray" else D.NonLocalMeans)(search_window_size=11, patch_size=5)
+    y = mod(img, h)
+    (y * g).sum().backward()
+    assert out_err(y.detach().cpu().numpy(), G[key + ".out"]) <= OUT_ATOL
+    assert_grad(h.grad.cpu().numpy(), G[key + ".gh"], 2e-4, f"{name} d/dh")   # the reference's own fp32 noise is ~5e-5
+
+
+def test_bare_nlm_modules_api(dev):
+    from adaptiveisp_b200 import AispError, denoise as D
+    with pytest.raises(AispError):
+        D.NonLocalMeansGray(search_window_size=21, patch_size=7)       # only the 11 / 5 configuration is built
+    with pytest.raises(NotImplementedError):
+        D.NonLocalMeansParam(0.5)
+    x = cases.lod_batch(2, 48, 64, seed=3, device=dev)
+    # scalar h shared by the batch: the gradient is summed over the samples
+    h = torch.tensor([0.3], device=dev, requires_grad=True)
+    y = D.NonLocalMeans(11, 5)(x, h)
+    y.sum().backward()
+    hb = torch.tensor([0.3, 0.3], device=dev).reshape(2, 1, 1, 1).requires_grad_(True)
+    yb = D.NonLocalMeans(11, 5)(x, hb)
+    yb.sum().backward()
+    assert torch.equal(y, yb) and abs(float(h.grad) - float(hb.grad.sum())) <= 1e-4 * abs(float(h.grad)) + 1e-6
+    with pytest.raises(AispError):
+        D.NonLocalMeansGray(11, 5)(x.clone().requires_grad_(True), h)
+    # the small helpers are the reference's torch statements
+    lum = D.rgb_to_luminance(x)
+    assert lum.shape == (2, 1, 48, 64)
+    assert D.BoxFilter(5, "sum")(lum).shape == lum.shape and D.ShiftStack(3)(lum).shape == (2, 1, 48, 64, 9)
