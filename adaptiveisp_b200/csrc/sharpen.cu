@@ -491,9 +491,12 @@ sharpen_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_c
 
 // ---------------------------------------------------------------------------------------------
 // transposed stencil: grad_img from the masked upstream gradient gy (staged by the kernel above)
-// CTA <-> (sample, 32x8 tile), one pixel per thread, all three planes.
+// CTA <-> (sample, 128x8 tile); a thread owns a 1x4 strip of all three planes and evaluates the transposed
+// stencil separably from registers (5 rows x 8 staged values per plane): the 5x5 Gaussian is k (x) k, the
+// 3x3 kernel is (ones3x3 + 4 delta) / 13.  Reflect-padding mirrors (USM, pixels within 2 of the frame) are
+// folded in per pixel from global memory -- a few pixels per row.
 // ---------------------------------------------------------------------------------------------
-constexpr int kAdjW = 32, kAdjH = 8;
+constexpr int kAdjW = 128, kAdjH = 8, kAdjSW = kAdjW + 8;   // staged row: tile column 0 at smem column 4
 
 __device__ __forceinline__ float gy_valid(const float* __restrict__ gy, int op, int H, int W, int y, int x) {
     // gradient of output pixel (y,x) that flows through its blur term
@@ -524,7 +527,7 @@ __global__ void __launch_bounds__(kThreads)
 sharpen_adjoint_kernel(const float* __restrict__ gy, float* __restrict__ gimg, const float* __restrict__ params,
                        const int32_t* __restrict__ ops, int H, int W) {
     pdl_prologue();
-    __shared__ float sm[3][kAdjH + 4][kAdjW + 4];
+    __shared__ float sm[3][kAdjH + 4][kAdjSW];
     __shared__ float sc[kConst];
     __shared__ float wk[5][5];
     const int b = blockIdx.z;
@@ -534,48 +537,80 @@ sharpen_adjoint_kernel(const float* __restrict__ gy, float* __restrict__ gimg, c
     const size_t base = (size_t)b * 3 * H * W;
     load_consts(params, b, op, sc);
     __syncthreads();
-    if (threadIdx.x < 25) {
+    if (threadIdx.x < 25) {   // dense 5x5 weights: only the mirror terms of frame pixels use them
         const int i = threadIdx.x / 5, j = threadIdx.x % 5;
         float v;
         if (op == AISP_OP_USM) v = sc[i] * sc[j];
         else v = (i == 0 || i == 4 || j == 0 || j == 4) ? 0.f : ((i == 2 && j == 2) ? 5.0f / 13.0f : 1.0f / 13.0f);
         wk[i][j] = v;
     }
-    for (int e = threadIdx.x; e < 3 * (kAdjH + 4) * (kAdjW + 4); e += kThreads) {
-        const int ch = e / ((kAdjH + 4) * (kAdjW + 4));
-        const int rem = e - ch * ((kAdjH + 4) * (kAdjW + 4));
-        const int row = rem / (kAdjW + 4), col = rem - row * (kAdjW + 4);
-        sm[ch][row][col] = gy_valid(gy + base + (size_t)ch * H * W, op, H, W, y0 - 2 + row, x0 - 2 + col);
+    constexpr int kCols = kAdjW + 4;   // staged columns x0-2 .. x0+kAdjW+1 live at smem columns 2 .. kAdjW+5
+    for (int e = threadIdx.x; e < 3 * (kAdjH + 4) * kCols; e += kThreads) {
+        const int ch = e / ((kAdjH + 4) * kCols);
+        const int rem = e - ch * ((kAdjH + 4) * kCols);
+        const int row = rem / kCols, col = rem - row * kCols;
+        sm[ch][row][col + 2] = gy_valid(gy + base + (size_t)ch * H * W, op, H, W, y0 - 2 + row, x0 - 2 + col);
     }
     __syncthreads();
-    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-    const int x = x0 + lx, y = y0 + ly;
-    if (x >= W || y >= H) return;
+    const int lx = (threadIdx.x & 31) * 4, ly = threadIdx.x >> 5;
+    const int xs = x0 + lx, y = y0 + ly;
+    if (xs >= W || y >= H) return;
     float alpha, beta;
     if (op == AISP_OP_SHARPEN) { alpha = sc[0]; beta = 1.0f - sc[0]; }
     else if (op == AISP_OP_SHARPEN_V2) { alpha = 1.0f + sc[0]; beta = -sc[0]; }
     else { alpha = 1.0f + sc[10]; beta = -sc[10]; }
-    const bool border = (x == 0) || (y == 0) || (x == W - 1) || (y == H - 1);
-    int my[2], mx[2];
-    const int nmy = (op == AISP_OP_USM) ? mirrors(y, H, my) : 0;
-    const int nmx = (op == AISP_OP_USM) ? mirrors(x, W, mx) : 0;
+    const bool usm = (op == AISP_OP_USM);
+    const float k0 = sc[0], k1 = sc[1], k2 = sc[2];
+    int my[2];
+    const int nmy = usm ? mirrors(y, H, my) : 0;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         const float* gch = gy + base + (size_t)ch * H * W;
-        float s = 0.f;
+        // rows y-2 .. y+2, columns xs-2 .. xs+5 of the masked gradient
+        float v[5][8];
 #pragma unroll
-        for (int dy = -2; dy <= 2; ++dy)
+        for (int r = 0; r < 5; ++r)
 #pragma unroll
-            for (int dx = -2; dx <= 2; ++dx) s = fmaf(wk[dy + 2][dx + 2], sm[ch][ly + 2 - dy][lx + 2 - dx], s);
-        // reflect padding folds the halo of the padded plane back onto its mirror pixels
-        for (int a = 0; a < nmy; ++a) s += gpad_at(gch, op, wk, H, W, my[a], x);
-        for (int c2 = 0; c2 < nmx; ++c2) s += gpad_at(gch, op, wk, H, W, y, mx[c2]);
-        for (int a = 0; a < nmy; ++a)
-            for (int c2 = 0; c2 < nmx; ++c2) s += gpad_at(gch, op, wk, H, W, my[a], mx[c2]);
-        const float g0 = gch[(size_t)y * W + x];
-        float v = alpha * g0 + beta * s;
-        if (op != AISP_OP_USM && border) v += beta * g0;
-        gimg[base + ((size_t)ch * H + y) * W + x] = v;
+            for (int i = 0; i < 8; ++i) v[r][i] = sm[ch][ly + r][lx + 2 + i];
+        float s[4];
+        if (usm) {
+            float hrow[5][4];
+#pragma unroll
+            for (int r = 0; r < 5; ++r)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    hrow[r][i] = fmaf(k0, v[r][i] + v[r][i + 4], fmaf(k1, v[r][i + 1] + v[r][i + 3], k2 * v[r][i + 2]));
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                s[i] = fmaf(k0, hrow[0][i] + hrow[4][i], fmaf(k1, hrow[1][i] + hrow[3][i], k2 * hrow[2][i]));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float box = 0.f;
+#pragma unroll
+                for (int r = 1; r < 4; ++r) box += (v[r][i + 1] + v[r][i + 2]) + v[r][i + 3];
+                s[i] = fmaf(4.0f / 13.0f, v[2][i + 2], box * (1.0f / 13.0f));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int x = xs + i;
+            if (x >= W) continue;
+            float si = s[i];
+            if (usm) {   // reflect padding folds the halo of the padded plane back onto its mirror pixels
+                int mx[2];
+                const int nmx = mirrors(x, W, mx);
+                for (int a = 0; a < nmy; ++a) si += gpad_at(gch, op, wk, H, W, my[a], x);
+                for (int c2 = 0; c2 < nmx; ++c2) si += gpad_at(gch, op, wk, H, W, y, mx[c2]);
+                for (int a = 0; a < nmy; ++a)
+                    for (int c2 = 0; c2 < nmx; ++c2) si += gpad_at(gch, op, wk, H, W, my[a], mx[c2]);
+            }
+            const float g0 = gch[(size_t)y * W + x];
+            float out = alpha * g0 + beta * si;
+            const bool border = (x == 0) || (y == 0) || (x == W - 1) || (y == H - 1);
+            if (!usm && border) out += beta * g0;
+            gimg[base + ((size_t)ch * H + y) * W + x] = out;
+        }
     }
 }
 
