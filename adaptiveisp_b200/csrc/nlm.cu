@@ -15,6 +15,7 @@
 //
 // When `dout_dh` is requested the same pass also accumulates sum(w*d) and sum(w*d*x), which give
 // d out / d h in closed form, so training never runs a second 121-shift pass.
+#include <cstdlib>
 #include "pointwise_math.cuh"   // fwd_px / stage_consts for the fused per-pixel prologue and epilogue (-fmad=false)
 
 namespace aisp {
@@ -331,6 +332,268 @@ nlm_kernel(const float* __restrict__ img, float* __restrict__ out, float* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two-columns-per-lane layout (round 2): lane l owns the ADJACENT staged columns 2l, 2l+1 of a 64-column
+// row group and two rows, so every per-pixel quantity of a thread is a natural {even column, odd column}
+// pair and the whole arithmetic runs as Blackwell packed fp32 (sub/mul/fma/add.f32x2: one issue slot per
+// two pixels) -- the kernel is bound by issue slots, not by the FMA pipe.  The 5-wide box sum needs three
+// shuffles per PAIR of pixels (pair sums P from lanes l+1, l+2 and the even column of lane l+2) instead of
+// three per pixel, lanes 0..29 of 32 produce outputs (60 of 64 columns), and the luma / RGB columns are
+// not cached per horizontal offset but slide through registers along dy (one new row per step).
+//   CTA <-> (sample, 60 x 16 tile); warp w owns rows 2w, 2w+1.
+//   Shared memory holds the staged tile twice, the second copy shifted by one float, so that the pair
+//   starting at ANY column is an aligned 64-bit load (even horizontal offsets read copy A, odd ones B).
+// ---------------------------------------------------------------------------------------------
+constexpr int kN2Rows = 2;                               // output rows per thread
+constexpr int kN2TW = 60, kN2TH = kN2Rows * kWarps;      // outputs per CTA
+constexpr int kN2SW = kN2TW + 2 * kNlmHalo;              // 74 staged columns  x0-7 .. x0+66
+constexpr int kN2SH = kN2TH + 2 * kNlmHalo;              // 30 staged rows     y0-7 .. y0+22
+constexpr int kN2RS = 76;                                // row stride in floats (even; copy A stores column s at s+1)
+constexpr int kN2Plane = kN2SH * kN2RS;
+constexpr int kN2Copy = 4 * kN2Plane;                    // planes: luma, R, G, B
+constexpr int kN2SmemBytes = 2 * kN2Copy * (int)sizeof(float);
+
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 lds2(const float* p) {   // 8-byte aligned pair from shared memory
+    return *reinterpret_cast<const f32x2*>(p);
+}
+
+template <bool WITH_GRAD, bool SEQ>
+__global__ void __launch_bounds__(kThreads, 3)
+nlm2_kernel(const float* __restrict__ img, float* __restrict__ out, float* __restrict__ dout_dh,
+            float* __restrict__ wsum_out, const float* __restrict__ params, const int32_t* __restrict__ ops, int H,
+            int W, BankMap bm, const int32_t* __restrict__ seq_len, int S, int clip_each, int variant, int vec8) {
+    pdl_prologue();
+    extern __shared__ __align__(16) float n2sm[];
+    __shared__ float sraw[SEQ ? AISP_MAX_STEPS : 1][kConst];
+    __shared__ float ssc[SEQ ? AISP_MAX_STEPS : 1][kConst];
+    __shared__ int ssop[SEQ ? AISP_MAX_STEPS : 1];
+    __shared__ int rownz[kN2SH];                 // staged row holds a non-zero value (zero shortcut: see nlm_kernel)
+    const int b = bank_sample(bm, blockIdx.z);
+    int pos = 0, len = 1;
+    if (SEQ) {
+        len = seq_len ? min(max(seq_len[b], 0), S) : S;
+        pos = find_stencil(ops + (size_t)b * S, len, &len);
+        if (pos < 0 || ops[(size_t)b * S + pos] != AISP_OP_NLM) return;   // another family owns this sample
+        stage_consts(params, ops, b, S, len, sraw, ssc, ssop, bm);
+    } else {
+        if (sample_op(ops, bm, b) != AISP_OP_NLM) return;
+    }
+    const int x0 = blockIdx.x * kN2TW, y0 = blockIdx.y * kN2TH;
+    const size_t plane = (size_t)H * W;
+    const float* src = img + (size_t)(b / bm.F) * 3 * plane;
+    const size_t sb = (size_t)(b / bm.F);        // stashes stay compact: one NLM slot per image
+    const float h = params[((size_t)b * (SEQ ? S : 1) + pos) * AISP_PSTRIDE];
+    const float hh = fmaxf(h, 0.f) + 1e-8f;              // relu(h) + EPS   (denoise.py:112)
+    const float negk = -1.4426950408889634f / hh;        // exp(-d/hh) = 2^(d * negk)
+
+    // stage the wrapped tile + halo (flat, fully unrolled: see nlm_kernel), both copies
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool wide = (W >= kN2SW) && (H >= kN2SH);
+    constexpr int kStageN = kN2SH * kN2SW;
+    constexpr int kStageIt = (kStageN + kThreads - 1) / kThreads;
+    if (threadIdx.x < kN2SH) rownz[threadIdx.x] = 0;
+    __syncthreads();
+    {
+        float vr[kStageIt], vg[kStageIt], vb[kStageIt];
+#pragma unroll
+        for (int it = 0; it < kStageIt; ++it) {
+            const int e = it * kThreads + threadIdx.x;
+            vr[it] = vg[it] = vb[it] = 0.f;
+            if (e < kStageN) {
+                const int row = e / kN2SW, col = e - row * kN2SW;
+                int gy = y0 - kNlmHalo + row, gx = x0 - kNlmHalo + col;
+                gy = wide ? (gy < 0 ? gy + H : (gy >= H ? gy - H : gy)) : wrap(gy, H);
+                gx = wide ? (gx < 0 ? gx + W : (gx >= W ? gx - W : gx)) : wrap(gx, W);
+                const float* rp = src + (size_t)gy * W + gx;
+                vr[it] = __ldg(rp);
+                vg[it] = __ldg(rp + plane);
+                vb[it] = __ldg(rp + 2 * plane);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < kStageIt; ++it) {
+            const int e = it * kThreads + threadIdx.x;
+            const int row = e / kN2SW, col = e - row * kN2SW;
+            float r = vr[it], g = vg[it], bl = vb[it];
+            if (SEQ) {
+                for (int k = 0; k < pos; ++k) {
+                    fwd_px<true>(ssop[k], ssc[k], r, g, bl);
+                    if (clip_each) { r = clip01(r); g = clip01(g); bl = clip01(bl); }
+                }
+            }
+            const float cr = clip01(r), cg = clip01(g), cb = clip01(bl);
+            float yy = (0.299f * cr + 0.587f * cg) + 0.114f * cb;
+            if (variant == 0) { r = cr; g = cg; bl = cb; }                       // the filter averages what it clipped
+            else if (variant >= 2) yy = (variant == 2) ? r : (variant == 3 ? g : bl);
+            const bool in = e < kStageN;
+            if (in) {
+                float* pa = n2sm + row * kN2RS + col + 1;
+                float* pb = n2sm + kN2Copy + row * kN2RS + col;
+                pa[0] = yy;            pb[0] = yy;
+                pa[kN2Plane] = r;      pb[kN2Plane] = r;
+                pa[2 * kN2Plane] = g;  pb[2 * kN2Plane] = g;
+                pa[3 * kN2Plane] = bl; pb[3 * kN2Plane] = bl;
+            }
+            const bool nz = in && ((r != 0.f) | (g != 0.f) | (bl != 0.f));
+            const unsigned any = __ballot_sync(0xffffffffu, nz);
+            const unsigned grp = __match_any_sync(0xffffffffu, in ? row : -1);
+            if (in && (any & grp) && lane == __ffs(grp) - 1) atomicOr(&rownz[row], 1);
+        }
+    }
+    __syncthreads();
+
+    const int r0 = warp * kN2Rows;               // first output row of this thread, relative to y0
+    // own luma pairs: staged rows r0+5 .. r0+10, staged columns 5+2l, 6+2l (copy A index 6+2l)
+    f32x2 yo[kN2Rows + 4];
+#pragma unroll
+    for (int j = 0; j < kN2Rows + 4; ++j) yo[j] = lds2(n2sm + (r0 + 5 + j) * kN2RS + 6 + 2 * lane);
+
+    f32x2 ac[3][kN2Rows], bc[3][kN2Rows], wsum2[kN2Rows], wd2[kN2Rows];
+#pragma unroll
+    for (int i = 0; i < kN2Rows; ++i) {
+        wsum2[i] = pack2(0.f, 0.f);
+        wd2[i] = pack2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { ac[c][i] = pack2(0.f, 0.f); bc[c][i] = pack2(0.f, 0.f); }
+    }
+
+    bool live = false;
+    for (int t = 0; t < kN2Rows + 2 * kNlmHalo; ++t) live |= (rownz[r0 + t] != 0);
+    live = __any_sync(0xffffffffu, live);
+
+    const f32x2 negk2 = pack2(negk, negk);
+    const int lc = min(lane, 29);                // lanes 30, 31 only feed the box sums: keep their RGB reads in range
+    // source offsets run +5 .. -5: terms are accumulated in the reference's order (denoise.py:106-109)
+    for (int dx = live ? 5 : -6; dx >= -5; --dx) {
+        const int odd = dx & 1;
+        const float* cpy = n2sm + odd * kN2Copy;
+        // pair starting at staged column s: copy A index s+1 (s odd), copy B index s (s even)
+        const float* yp = cpy + r0 * kN2RS + (6 + 2 * lane + dx - odd);                      // luma rows r0 .. r0+15
+        const float* cp = cpy + kN2Plane + (r0 + 2) * kN2RS + (8 + 2 * lc + dx - odd);       // RGB rows r0+2 .. r0+13
+        f32x2 yw[kN2Rows + 14];
+        f32x2 cw[3][kN2Rows + 10];
+#pragma unroll
+        for (int j = 0; j < kN2Rows + 4; ++j) yw[j + 10] = lds2(yp + (j + 10) * kN2RS);
+#pragma unroll
+        for (int i = 0; i < kN2Rows; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) cw[c][i + 10] = lds2(cp + c * kN2Plane + (i + 10) * kN2RS);
+#pragma unroll
+        for (int dy = 5; dy >= -5; --dy) {
+            if (dy > -5) {   // the rows the next step slides in
+                yw[dy + 4] = lds2(yp + (dy + 4) * kN2RS);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) cw[c][dy + 4] = lds2(cp + c * kN2Plane + (dy + 4) * kN2RS);
+            }
+            f32x2 t[kN2Rows + 4];
+#pragma unroll
+            for (int j = 0; j < kN2Rows + 4; ++j) t[j] = sub2(yo[j], yw[j + dy + 5]);
+            f32x2 m = mul2(t[1], t[1]);
+            m = fma2(t[2], t[2], m);
+            m = fma2(t[3], t[3], m);
+            m = fma2(t[4], t[4], m);
+            f32x2 v[kN2Rows];
+            v[0] = fma2(t[0], t[0], m);
+            v[1] = fma2(t[5], t[5], m);
+#pragma unroll
+            for (int i = 0; i < kN2Rows; ++i) {
+                // windows of five columns starting at the lane's own even / odd column
+                const float ve = lo2(v[i]), vo = hi2(v[i]);
+                const float pr = ve + vo;
+                const float s1 = __shfl_down_sync(0xffffffffu, pr, 1);
+                const float s2 = __shfl_down_sync(0xffffffffu, pr, 2);
+                const float e2 = __shfl_down_sync(0xffffffffu, ve, 2);
+                const float ba = (pr + s1) + e2, bb = (vo + s1) + s2;
+                // box >= 0: the reference's relu is a no-op
+                const f32x2 dist = pack2(sqrt_approx(ba), sqrt_approx(bb));
+                const f32x2 arg = mul2(dist, negk2);
+                const f32x2 ww = pack2(ex2_approx(lo2(arg)), ex2_approx(hi2(arg)));
+                wsum2[i] = add2(wsum2[i], ww);
+                const int u = i + dy + 5;
+                ac[0][i] = fma2(ww, cw[0][u], ac[0][i]);
+                ac[1][i] = fma2(ww, cw[1][u], ac[1][i]);
+                ac[2][i] = fma2(ww, cw[2][u], ac[2][i]);
+                if (WITH_GRAD) {
+                    const f32x2 wdi = mul2(ww, dist);
+                    wd2[i] = add2(wd2[i], wdi);
+                    bc[0][i] = fma2(wdi, cw[0][u], bc[0][i]);
+                    bc[1][i] = fma2(wdi, cw[1][u], bc[1][i]);
+                    bc[2][i] = fma2(wdi, cw[2][u], bc[2][i]);
+                }
+            }
+        }
+    }
+
+    const int gx = x0 + 2 * lane;
+    if (lane >= kN2TW / 2 || gx >= W) return;
+    const float gcoef = (h > 0.f) ? 1.0f / (hh * hh) : 0.f;  // relu'(h) / hh^2
+    const bool two = gx + 1 < W;
+    const bool vec = two && vec8;                // 8-byte aligned pairs: even row length, aligned bases (host-checked)
+#pragma unroll
+    for (int i = 0; i < kN2Rows; ++i) {
+        const int gy = y0 + r0 + i;
+        if (gy >= H) continue;
+        float ws[2] = {lo2(wsum2[i]), hi2(wsum2[i])};
+        if (!live) ws[0] = ws[1] = 121.0f;       // all 121 weights are exactly 1
+        const float wdv[2] = {lo2(wd2[i]), hi2(wd2[i])};
+        const size_t px = (size_t)gy * W + gx;
+        float yv[2][3], dv[2][3];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float iw = 1.0f / ws[k];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float a = k ? hi2(ac[c][i]) : lo2(ac[c][i]);
+                float y = a * iw;
+                if (variant == 0) {   // 0 * x: the (1 - mask) * img term of the reference's lerp (see nlm_kernel)
+                    const float xin = (SEQ && pos > 0)
+                                          ? n2sm[(1 + c) * kN2Plane + (r0 + i + kNlmHalo) * kN2RS + 8 + 2 * lane + k]
+                                          : ((k == 0 || two) ? __ldg(src + (size_t)c * plane + px + k) : 0.f);
+                    y = fmaf(0.f, xin, y);
+                }
+                yv[k][c] = clip01(y);
+                if (WITH_GRAD) {
+                    const float bcv = k ? hi2(bc[c][i]) : lo2(bc[c][i]);
+                    dv[k][c] = pass01(y) * (bcv - y * wdv[k]) * iw * gcoef;
+                }
+            }
+            if (SEQ) {
+                for (int q = pos + 1; q < len; ++q) {
+                    fwd_px<true>(ssop[q], ssc[q], yv[k][0], yv[k][1], yv[k][2]);
+                    if (clip_each) { yv[k][0] = clip01(yv[k][0]); yv[k][1] = clip01(yv[k][1]); yv[k][2] = clip01(yv[k][2]); }
+                }
+            }
+        }
+        if (wsum_out) {
+            float* wp = wsum_out + sb * plane + px;
+            if (vec) *reinterpret_cast<float2*>(wp) = make_float2(ws[0], ws[1]);
+            else { wp[0] = ws[0]; if (two) wp[1] = ws[1]; }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (!(variant < 2 || c == variant - 2)) continue;
+            float* op = out + (size_t)b * 3 * plane + (size_t)c * plane + px;
+            if (vec) *reinterpret_cast<float2*>(op) = make_float2(yv[0][c], yv[1][c]);
+            else { op[0] = yv[0][c]; if (two) op[1] = yv[1][c]; }
+            if (WITH_GRAD) {
+                float* dp = dout_dh + sb * 3 * plane + (size_t)c * plane + px;
+                if (vec) *reinterpret_cast<float2*>(dp) = make_float2(dv[0][c], dv[1][c]);
+                else { dp[0] = dv[0][c]; if (two) dp[1] = dv[1][c]; }
+            }
+        }
+    }
+}
+
 // grad_h[b] = sum g * dout_dh : plain streaming dot product, chunked like the per-pixel kernels
 __global__ void __launch_bounds__(kThreads)
 nlm_dot_kernel(const float* __restrict__ gout, const float* __restrict__ stash, const int32_t* __restrict__ ops,
@@ -372,11 +635,44 @@ cudaError_t launch_finalize(const float* partial, int nrows, const float* params
                             int B, float* grad_params, BankMap bm, cudaStream_t st);
 int pointwise_rows(int H, int W);
 
+// A/B switch for measurements: AISP_NLM_LAYOUT=1col selects the one-column-per-lane kernel (nlm_kernel)
+static bool nlm_one_column_layout() {
+    static const int v = [] {
+        const char* e = getenv("AISP_NLM_LAYOUT");
+        return (e && e[0] == '1') ? 1 : 0;
+    }();
+    return v != 0;
+}
+
 // one NLM forward over [B,3,H,W]: 28-wide tiles, a remainder of <= 12 columns goes to the half-warp layout
 // (12 columns x 64 rows per CTA).  seq == true: per-sample sequences (see nlm_kernel<.., SEQ>).
 static cudaError_t launch_nlm_any(const float* img, float* out, const float* params, const int32_t* ops, int B, int H,
                                   int W, float* dout_dh, float* wsum, BankMap bm, bool seq, const int32_t* seq_len,
                                   int S, int clip_each, int variant, cudaStream_t st) {
+    if (!nlm_one_column_layout()) {
+        // two-columns-per-lane layout: 60 x 16 tiles cover every width, no remainder launch
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(nlm2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kN2SmemBytes);
+            cudaFuncSetAttribute(nlm2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kN2SmemBytes);
+            cudaFuncSetAttribute(nlm2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kN2SmemBytes);
+            attr_done = true;
+        }
+        const uintptr_t bases = reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dout_dh) |
+                                reinterpret_cast<uintptr_t>(wsum);
+        const int vec8 = ((W & 1) == 0) && ((bases & 7u) == 0);
+        dim3 grid((W + kN2TW - 1) / kN2TW, (H + kN2TH - 1) / kN2TH, B);
+        if (seq)
+            launch_pdl_smem(nlm2_kernel<false, true>, grid, kThreads, kN2SmemBytes, st, img, out, nullptr, nullptr, params,
+                            ops, H, W, bm, seq_len, S, clip_each, variant, vec8);
+        else if (dout_dh)
+            launch_pdl_smem(nlm2_kernel<true, false>, grid, kThreads, kN2SmemBytes, st, img, out, dout_dh, wsum, params, ops,
+                            H, W, bm, nullptr, 1, 0, variant, vec8);
+        else
+            launch_pdl_smem(nlm2_kernel<false, false>, grid, kThreads, kN2SmemBytes, st, img, out, nullptr, wsum, params, ops,
+                            H, W, bm, nullptr, 1, 0, variant, vec8);
+        return cudaGetLastError();
+    }
     using G32 = NlmGeo<32>;
     using G16 = NlmGeo<16>;
     int n32 = W / G32::TW;

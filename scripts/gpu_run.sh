@@ -1,0 +1,28 @@
+#!/bin/bash
+# one GPU call: scripts/gpu_run.sh TAG [tests] [bench] [nlm_ab] ...  (logs land in gpurun_out/TAG_*)
+set -u
+TAG=$1; shift
+OUT=gpurun_out
+mkdir -p $OUT
+for what in "$@"; do
+  case $what in
+    tests)
+      timeout 1200 python -m pytest tests/test_gpu_round2.py -q -m gpu -x 2>&1 | tail -60 > $OUT/${TAG}_tests_new.log
+      timeout 1500 python -m pytest tests/test_gpu_parity.py -q -m gpu -x 2>&1 | tail -60 > $OUT/${TAG}_tests_old.log
+      tail -3 $OUT/${TAG}_tests_new.log; tail -3 $OUT/${TAG}_tests_old.log;;
+    nlmtests)
+      timeout 1200 python -m pytest tests -q -m gpu -x -k "nlm or NLM or denoise or bank or smoke or config" 2>&1 | tail -60 > $OUT/${TAG}_tests_nlm.log
+      tail -5 $OUT/${TAG}_tests_nlm.log;;
+    bench)
+      timeout 900 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+      tail -c 300 $OUT/${TAG}_bench.err;;
+    nlm_ab)
+      AISP_NLM_LAYOUT=1col timeout 300 python scripts/micro/nlm_ab.py 2>&1 | tee $OUT/${TAG}_nlm_ab.log
+      timeout 300 python scripts/micro/nlm_ab.py 2>&1 | tee -a $OUT/${TAG}_nlm_ab.log;;
+    ncu_nlm)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:nlm2_kernel -s 3 -c 1 -f -o $OUT/prof_nlm2_${TAG} \
+          python scripts/micro/nlm_ab.py > $OUT/${TAG}_ncu_nlm.log 2>&1
+      tail -3 $OUT/${TAG}_ncu_nlm.log;;
+    *) echo "unknown step $what";;
+  esac
+done
