@@ -129,7 +129,7 @@ __device__ __forceinline__ float min_nan(float a, float b) {
     return r;
 }
 // clamp backward: gradient passes iff lo <= y <= hi, inclusive (NaN -> 0)
-__device__ __forceinline__ float pass01(float y) { return (y >= 0.f && y <= 1.f) ? 1.f : 0.f; }
+__device__ __forceinline__ float pass01(float y) { return (__saturatef(y) == y) ? 1.f : 0.f; }   // see mask01
 
 // ---------------------------------------------------------------------------------------------
 // per-step derived constants (one thread per step computes them once per CTA / finalize block)

@@ -37,6 +37,7 @@ cudaError_t launch_regress(const float*, const int32_t*, const int32_t*, int, in
                            float*, cudaStream_t);
 cudaError_t launch_value_stats(const float*, int, int, float*, cudaStream_t);
 cudaError_t launch_nlm_module_fwd(const float*, float*, const float*, const int32_t*, int, int, int, float*, int, cudaStream_t);
+cudaError_t launch_nlm_param_fwd(const float*, const float*, float*, float*, const float*, int, int, int, int, cudaStream_t);
 bool pointwise_can_emit(int, int, int, int);
 bool sharpen_can_emit(int, int, int, int);
 int chain_bwd_max_steps();
@@ -151,6 +152,16 @@ int aisp_nlm_module_fwd(const float* img, float* out, const float* params, const
     if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
     if (img == out) return AISP_ERR_UNSUPPORTED;
     return (int)launch_nlm_module_fwd(img, out, params, ops, B, H, W, dout_dh, gray ? 1 : 0, (cudaStream_t)stream);
+}
+
+int aisp_nlm_param_fwd(const float* rgb, const float* luma, float* out, float* dout_dh, const float* h, int B, int H,
+                       int W, int window, void* stream) {
+    if (!rgb || !luma || !out || !h) return AISP_ERR_NULL;
+    if (!shape_ok(B, H, W)) return AISP_ERR_SHAPE;
+    // reflect padding needs pad < size (as F.pad does); windows are odd
+    if (window < 1 || (window & 1) == 0 || window / 2 >= H || window / 2 >= W) return AISP_ERR_SHAPE;
+    if (rgb == out) return AISP_ERR_UNSUPPORTED;
+    return (int)launch_nlm_param_fwd(rgb, luma, out, dout_dh, h, B, H, W, window, (cudaStream_t)stream);
 }
 
 int aisp_nlm_bwd(const float* grad_out, const float* dout_dh, const int32_t* ops, int B, int H, int W,

@@ -20,6 +20,7 @@
 // instantiation with 27-wide accumulators launched with ONE CTA per sample (it walks the sample's
 // chunks); the main instantiation skips those samples and vice versa, so ColorFilter costs the common
 // sequences nothing.
+#include <cstdlib>
 #include "pointwise_math.cuh"
 
 namespace aisp {
@@ -134,6 +135,209 @@ __device__ __forceinline__ int classify_sequence(const int32_t* __restrict__ ops
     return len;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Compile-time sequences.  A sequence that is known when the library is built gets its own kernel: the op
+// dispatch, the shared-memory parking and the padded accumulator rows of the generic kernel disappear
+// (every stage input lives in registers, a stage owns exactly the partial sums its op has), and the
+// compiler schedules forward recomputation and reverse sweep as one straight-line block.  Registered:
+// the per-pixel prefix of the reference's fixed pipeline (BASELINE configs[0], isp/filters.py:753-815):
+// exposure -> gamma -> white balance -> CCM.  A sample whose sequence is exactly a registered one is served
+// by that kernel and skipped by the generic one; both are always launched (the ops live on the device).
+// ---------------------------------------------------------------------------------------------
+template <int... OPS>
+struct OpSeq {
+    static constexpr int N = sizeof...(OPS);
+    __host__ __device__ static constexpr int at(int k) {
+        constexpr int v[N] = {OPS...};
+        return v[k];
+    }
+    static __device__ __forceinline__ bool matches(const int32_t* __restrict__ o, int len) {
+        if (len != N) return false;
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < N; ++k) ok &= (o[k] == at(k));
+        return ok;
+    }
+};
+using SeqEGWC = OpSeq<AISP_OP_EXPOSURE, AISP_OP_GAMMA, AISP_OP_WB, AISP_OP_CCM>;
+
+// true when a compile-time instantiation owns this (already classified, per-pixel only) sequence
+__device__ __forceinline__ bool owned_by_fixed(const int32_t* __restrict__ o, int len) {
+    return SeqEGWC::matches(o, len);
+}
+
+// clip of a recomputed stage output on the FMA pipe: sat(y) + 0 * y is clip(y) for finite y and NaN for a
+// non-finite one (what the reference's saved activation holds: its lerp term 0 * x poisons the pixel)
+__device__ __forceinline__ float clip_next(float y) { return fmaf(0.f, y, __saturatef(y)); }
+
+// reverse sweep from stage K down to stage 0 (compile-time recursion: the op is a template argument)
+constexpr int kFixedPx = 2;   // pixels a thread carries through forward + reverse sweep at a time (half a ring vector)
+// clamp mask of a stage output as an all-ones / all-zeros word, taken in the forward sweep and ANDed onto the
+// gradient in the reverse sweep: a value in a register, not a predicate that has to survive the sweep
+// (inline PTX: written in C the compiler turns the word back into a predicate and then packs 18 of them into
+// a register bit by bit)
+__device__ __forceinline__ unsigned clip_pass_bits(float y) {
+    unsigned m;
+    asm("set.eq.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(__saturatef(y)), "f"(y));   // FSET: 0xffffffff / 0, false for NaN
+    return m;
+}
+__device__ __forceinline__ float and_bits(float g, unsigned m) {
+    float r;
+    asm("and.b32 %0, %1, %2;" : "=f"(r) : "f"(g), "r"(m));
+    return r;
+}
+
+template <typename SEQ, int K, bool GIMG, bool CLIP>
+__device__ __forceinline__ void fixed_reverse(const float (*sc)[kConst], const float (&X)[SEQ::N][3][kFixedPx],
+                                              const unsigned (&M)[SEQ::N][3][kFixedPx], float (&gr)[kFixedPx],
+                                              float (&gg)[kFixedPx], float (&gb)[kFixedPx], float (&acc)[SEQ::N][9]) {
+    // the last stage's output only exists here: its body masks; earlier stages use the forward sweep's masks
+    constexpr int MODE = !CLIP ? 0 : (K == SEQ::N - 1 ? 1 : 2);
+#pragma unroll
+    for (int v = 0; v < kFixedPx; ++v) {
+        if (MODE == 2) { gr[v] = and_bits(gr[v], M[K][0][v]); gg[v] = and_bits(gg[v], M[K][1][v]); gb[v] = and_bits(gb[v], M[K][2][v]); }
+        PwBwd<SEQ::at(K)>::template px<(K > 0) || GIMG, MODE>(sc[K], X[K][0][v], X[K][1][v], X[K][2][v], gr[v], gg[v], gb[v],
+                                                              acc[K]);
+    }
+    if constexpr (K > 0) fixed_reverse<SEQ, K - 1, GIMG, CLIP>(sc, X, M, gr, gg, gb, acc);
+}
+
+template <int VEC, bool GIMG, bool CLIP, typename SEQ, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+pw_chain_fixed_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, const float* __restrict__ params,
+                          const int32_t* __restrict__ ops, const int32_t* __restrict__ seq_len, int N, int S, int flags,
+                          int rounds, int nchunks, float* __restrict__ gimg, float* __restrict__ partial) {
+    pdl_prologue();
+    extern __shared__ float4 dyn4[];
+    float4* ring = dyn4;                               // [2 slots][6 planes: x r,g,b then g r,g,b][kThreads]
+    constexpr int L = SEQ::N;
+    __shared__ float raw[L][kConst];
+    __shared__ float sc[L][kConst];
+    __shared__ int sop[L];
+    __shared__ float red[kWarps * AISP_ACC_STRIDE];
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x;
+    int fill;
+    const int len = classify_sequence(ops, seq_len, b, S, (flags & 2) != 0, false, &fill);
+    if (len == 0 || !SEQ::matches(ops + (size_t)b * S, len)) return;   // the generic kernel owns (or fills) the sample
+    stage_consts(params, ops, b, S, len, raw, sc, sop, BankMap{1, 0, 0ull, 0ull});
+    const size_t base = (size_t)b * 3 * (size_t)N;
+    const int chunk_px = rounds * kRoundPx;
+    const float* pr = img + base;
+    const float* pg = gout + base;
+    float* gi = GIMG ? gimg + base : nullptr;
+
+    for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const int chunk0 = chunk * chunk_px;
+        float acc[L][9];
+#pragma unroll
+        for (int k = 0; k < L; ++k)
+#pragma unroll
+            for (int j = 0; j < 9; ++j) acc[k][j] = 0.f;
+
+        // this thread's six vectors of round r -> ring slot (r & 1).  VEC == 4: one running element offset per
+        // thread, clamped so that the address of a (zero-filled) copy past the end stays inside the image
+        auto issue = [&](int r) {
+            const int i = chunk0 + (r * kThreads + tid) * kChainPx;
+            float4* slot = ring + (size_t)(r & 1) * 6 * kThreads + tid;
+            if (r < rounds) {
+                if (VEC == 4) {
+                    const bool ok = i < N;
+                    const float* p0 = pr + (ok ? i : 0);
+                    const float* g0 = pg + (ok ? i : 0);
+#pragma unroll
+                    for (int pl = 0; pl < 3; ++pl) {
+                        cp_async16_zfill(slot + pl * kThreads, p0 + (size_t)pl * N, ok);
+                        cp_async16_zfill(slot + (3 + pl) * kThreads, g0 + (size_t)pl * N, ok);
+                    }
+                } else {
+#pragma unroll
+                    for (int pl = 0; pl < 3; ++pl) {
+#pragma unroll
+                        for (int v = 0; v < kChainPx; ++v) {
+                            const bool ok = i + v < N;
+                            cp_async4_zfill(reinterpret_cast<float*>(slot + pl * kThreads) + v,
+                                            ok ? pr + (size_t)pl * N + i + v : pr, ok);
+                            cp_async4_zfill(reinterpret_cast<float*>(slot + (3 + pl) * kThreads) + v,
+                                            ok ? pg + (size_t)pl * N + i + v : pg, ok);
+                        }
+                    }
+                }
+            }
+            cp_async_commit();
+        };
+
+        issue(0);
+        for (int r = 0; r < rounds; ++r) {
+            issue(r + 1);
+            cp_async_wait<1>();
+            const int i = chunk0 + (r * kThreads + tid) * kChainPx;
+            if (i >= N) continue;
+            const float2* slot = reinterpret_cast<const float2*>(ring + (size_t)(r & 1) * 6 * kThreads + tid);
+            // the four pixels of the ring vector go through forward + reverse sweep two at a time: half the
+            // live stage inputs, and the loop body (not unrolled) is half the code
+#pragma unroll 1
+            for (int hv = 0; hv < kChainPx / kFixedPx; ++hv) {
+                const int i2 = i + hv * kFixedPx;
+                float X[L][3][kFixedPx];   // X[k] = input of stage k (X[0] straight from the ring)
+                unsigned M[L][3][kFixedPx];   // clamp mask of stage k's output (stages 0 .. L-2)
+#pragma unroll
+                for (int pl = 0; pl < 3; ++pl) {
+                    const float2 a = slot[2 * pl * kThreads + hv];
+                    X[0][pl][0] = a.x; X[0][pl][1] = a.y;
+                }
+                if (VEC == 1) {   // ragged tail: pixels past the end repeat a real pixel (and get a zero gradient below)
+                    if (i2 >= N) { X[0][0][0] = 0.5f; X[0][1][0] = 0.5f; X[0][2][0] = 0.5f; }
+                    if (i2 + 1 >= N) { X[0][0][1] = X[0][0][0]; X[0][1][1] = X[0][1][0]; X[0][2][1] = X[0][2][0]; }
+                }
+#pragma unroll
+                for (int k = 0; k + 1 < L; ++k) {
+#pragma unroll
+                    for (int v = 0; v < kFixedPx; ++v) {
+                        float r_ = X[k][0][v], g_ = X[k][1][v], b_ = X[k][2][v];
+                        fwd_px<false>(SEQ::at(k), sc[k], r_, g_, b_);
+                        X[k + 1][0][v] = CLIP ? clip_next(r_) : r_;
+                        X[k + 1][1][v] = CLIP ? clip_next(g_) : g_;
+                        X[k + 1][2][v] = CLIP ? clip_next(b_) : b_;
+                        if (CLIP) { M[k][0][v] = clip_pass_bits(r_); M[k][1][v] = clip_pass_bits(g_); M[k][2][v] = clip_pass_bits(b_); }
+                    }
+                }
+                float gr[kFixedPx], gg[kFixedPx], gb[kFixedPx];
+                {
+                    const float2 a = slot[2 * 3 * kThreads + hv], c = slot[2 * 4 * kThreads + hv], d = slot[2 * 5 * kThreads + hv];
+                    gr[0] = a.x; gr[1] = a.y;
+                    gg[0] = c.x; gg[1] = c.y;
+                    gb[0] = d.x; gb[1] = d.y;
+                }
+                if (VEC == 1) {
+#pragma unroll
+                    for (int v = 0; v < kFixedPx; ++v)
+                        if (i2 + v >= N) { gr[v] = 0.f; gg[v] = 0.f; gb[v] = 0.f; }
+                }
+                fixed_reverse<SEQ, L - 1, GIMG, CLIP>(sc, X, M, gr, gg, gb, acc);
+                if (GIMG) {
+                    if (VEC == 4) {
+                        *reinterpret_cast<float2*>(gi + i2) = make_float2(gr[0], gr[1]);
+                        *reinterpret_cast<float2*>(gi + N + i2) = make_float2(gg[0], gg[1]);
+                        *reinterpret_cast<float2*>(gi + 2 * (size_t)N + i2) = make_float2(gb[0], gb[1]);
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < kFixedPx; ++v)
+                            if (i2 + v < N) { gi[i2 + v] = gr[v]; gi[(size_t)N + i2 + v] = gg[v]; gi[2 * (size_t)N + i2 + v] = gb[v]; }
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+            __syncthreads();   // `red` is reused stage after stage (and chunk after chunk)
+            block_reduce_store_n<9>(acc[k], op_nacc(SEQ::at(k)), red,
+                                    partial + (((size_t)b * nchunks + chunk) * S + k) * AISP_ACC_STRIDE);
+        }
+    }
+}
+
 template <int VEC, bool GIMG, int SMAX, int NACC, bool CLIP>
 __global__ void __launch_bounds__(kThreads, NACC == 9 ? 2 : 1)
 pw_chain_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, const float* __restrict__ params,
@@ -156,6 +360,7 @@ pw_chain_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gou
     const int len = classify_sequence(ops, seq_len, b, S, strict, WITH_COLOR, &fill);
     const size_t base = (size_t)b * 3 * (size_t)N;
     const int chunk_px = rounds * kRoundPx;
+    if (len != 0 && !WITH_COLOR && owned_by_fixed(ops + (size_t)b * S, len)) return;   // a compile-time instantiation's
     if (len == 0) {
         // the filling is done by the main instantiation only (the ColorFilter one would repeat it)
         if (GIMG && fill != 0 && !WITH_COLOR) {
@@ -372,6 +577,27 @@ static cudaError_t launch_one(dim3 grid, cudaStream_t st, const float* img, cons
     return cudaGetLastError();
 }
 
+template <int VEC, bool GIMG, bool CLIP, typename SEQ, int MINB>
+static cudaError_t launch_fixed(dim3 grid, cudaStream_t st, const float* img, const float* gout, const float* params,
+                                const int32_t* ops, const int32_t* seq_len, int N, int S, int flags, int rounds,
+                                int nchunks, float* gimg, float* partial) {
+    constexpr size_t smem = (size_t)(2 * 6) * kThreads * sizeof(float4);
+    auto kern = pw_chain_fixed_bwd_kernel<VEC, GIMG, CLIP, SEQ, MINB>;
+    static bool attr_set_on[64] = {};
+    int devi = 0;
+    cudaGetDevice(&devi);
+    bool& attr_set = attr_set_on[devi & 63];
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_set = true;
+    }
+    launch_pdl_smem(kern, grid, kThreads, smem, st, img, gout, params, ops, seq_len, N, S, flags, rounds, nchunks, gimg,
+                    partial);
+    return cudaGetLastError();
+}
+
 // rows of scratch per sample and stage for an H x W image (the launcher below uses the same rule)
 static inline int chain_rounds(long long N, int B) {
     // 8 rounds per CTA (8192 px) amortise the per-chunk reduction; small problems keep 4 so that
@@ -412,6 +638,25 @@ cudaError_t launch_pointwise_chain_bwd(const float* img, const float* gout, cons
     }
 #undef AISP_LAUNCH
     if (e != cudaSuccess) return e;
+    // compile-time sequences (samples the generic kernel skipped)
+    if (S >= SeqEGWC::N) {
+        static const bool minb3 = [] { const char* e = getenv("AISP_CHAIN_MINB"); return e && e[0] == '3'; }();
+#define AISP_LAUNCH_FIXED(VEC, GIMG, CLIP)                                                                              \
+    (minb3 ? launch_fixed<VEC, GIMG, CLIP, SeqEGWC, 3>(grid, st, img, gout, params, ops, seq_len, (int)N, S, flags, rounds, \
+                                                       nchunks, grad_img, partial)                                      \
+           : launch_fixed<VEC, GIMG, CLIP, SeqEGWC, 4>(grid, st, img, gout, params, ops, seq_len, (int)N, S, flags, rounds, \
+                                                       nchunks, grad_img, partial))
+        const bool clip = (flags & AISP_SEQ_CLIP) != 0;
+        if (vec) {
+            if (grad_img) e = clip ? AISP_LAUNCH_FIXED(4, true, true) : AISP_LAUNCH_FIXED(4, true, false);
+            else          e = clip ? AISP_LAUNCH_FIXED(4, false, true) : AISP_LAUNCH_FIXED(4, false, false);
+        } else {
+            if (grad_img) e = clip ? AISP_LAUNCH_FIXED(1, true, true) : AISP_LAUNCH_FIXED(1, true, false);
+            else          e = clip ? AISP_LAUNCH_FIXED(1, false, true) : AISP_LAUNCH_FIXED(1, false, false);
+        }
+#undef AISP_LAUNCH_FIXED
+        if (e != cudaSuccess) return e;
+    }
     launch_pdl(chain_finalize_kernel, dim3(B, S), kThreads, st, partial, nchunks, S, flags, params, ops, seq_len,
                grad_params);
     return cudaGetLastError();

@@ -594,6 +594,76 @@ nlm2_kernel(const float* __restrict__ img, float* __restrict__ out, float* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// NonLocalMeansParam (isp/denoise.py:122-157): the unfold / reflect-pad variant with one learnable h.
+// Used nowhere in the reference, so this is a plain (not a fast) kernel: one output pixel per thread,
+//   D(p, s) = sum_{o in window} dis(reflect(p + o), s),  dis(q, s) = (Y(q) - Y(reflect(q + s)))^2
+// -- the reference pads the luma by reflection (:136), forms dis at the UNPADDED positions (:142), pads
+// dis by reflection (:144) and box-sums it over the SEARCH window size (:145-146: the patch is as large
+// as the search window) --, weights exp(-sqrt(D) / (relu(h) + EPS)), average of the reflect-padded rgb.
+// `luma` is rgb_to_luminance(rgb) (the luma of the clipped image).  dout_dh: closed form as in nlm_kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect_idx(int i, int n) {   // F.pad(mode='reflect'): -1 -> 1, n -> n - 2 (pad < n)
+    i = i < 0 ? -i : i;
+    return i >= n ? 2 * (n - 1) - i : i;
+}
+
+__global__ void __launch_bounds__(kThreads)
+nlm_param_kernel(const float* __restrict__ rgb, const float* __restrict__ luma, float* __restrict__ out,
+                 float* __restrict__ dout_dh, const float* __restrict__ hptr, int H, int W, int r) {
+    pdl_prologue();
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const size_t plane = (size_t)H * W;
+    const float* Y = luma + (size_t)b * plane;
+    const float* X = rgb + (size_t)b * 3 * plane;
+    const float h = hptr[0];
+    const float hh = fmaxf(h, 0.f) + 1e-8f;
+    float ws = 0.f, wd = 0.f, a[3] = {0.f, 0.f, 0.f}, bc[3] = {0.f, 0.f, 0.f};
+    for (int sy = -r; sy <= r; ++sy)
+        for (int sx = -r; sx <= r; ++sx) {
+            float box = 0.f;
+            for (int oy = -r; oy <= r; ++oy) {
+                const int qy = reflect_idx(y + oy, H);
+                const int ty = reflect_idx(qy + sy, H);
+                for (int ox = -r; ox <= r; ++ox) {
+                    const int qx = reflect_idx(x + ox, W);
+                    const int tx = reflect_idx(qx + sx, W);
+                    const float t = __ldg(Y + (size_t)qy * W + qx) - __ldg(Y + (size_t)ty * W + tx);
+                    box = fmaf(t, t, box);
+                }
+            }
+            const float d = sqrtf(fmaxf(box, 0.f));
+            const float w = __expf(-d / hh);
+            const size_t src = (size_t)reflect_idx(y + sy, H) * W + reflect_idx(x + sx, W);
+            ws += w;
+            wd = fmaf(w, d, wd);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v = __ldg(X + (size_t)c * plane + src);
+                a[c] = fmaf(w, v, a[c]);
+                bc[c] = fmaf(w * d, v, bc[c]);
+            }
+        }
+    const float iw = 1.0f / ws;
+    const float gcoef = (h > 0.f) ? 1.0f / (hh * hh) : 0.f;
+    const size_t px = (size_t)y * W + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float v = a[c] * iw;
+        out[(size_t)b * 3 * plane + (size_t)c * plane + px] = clip01(v);
+        if (dout_dh) dout_dh[(size_t)b * 3 * plane + (size_t)c * plane + px] = pass01(v) * (bc[c] - v * wd) * iw * gcoef;
+    }
+}
+
+cudaError_t launch_nlm_param_fwd(const float* rgb, const float* luma, float* out, float* dout_dh, const float* h, int B,
+                                 int H, int W, int window, cudaStream_t st) {
+    dim3 grid((W + 31) / 32, (H + 7) / 8, B);
+    launch_pdl(nlm_param_kernel, grid, kThreads, st, rgb, luma, out, dout_dh, h, H, W, window / 2);
+    return cudaGetLastError();
+}
+
 // grad_h[b] = sum g * dout_dh : plain streaming dot product, chunked like the per-pixel kernels
 __global__ void __launch_bounds__(kThreads)
 nlm_dot_kernel(const float* __restrict__ gout, const float* __restrict__ stash, const int32_t* __restrict__ ops,

@@ -30,9 +30,18 @@ __device__ __forceinline__ float ex2_mufu(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// bare MUFU reciprocal for arguments known to be normal (gamma: x >= 0.001): __fdividef wraps the same
+// MUFU in denormal-range scaling code (five more instructions per call)
+__device__ __forceinline__ float rcp_mufu(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // clamp backward as ATen does it (where(lo <= y <= hi, g, 0)): a select, so a non-finite upstream
 // gradient on a clipped pixel is dropped, not turned into NaN
-__device__ __forceinline__ float mask01(float y, float g) { return (y >= 0.f && y <= 1.f) ? g : 0.f; }
+// 0 <= y <= 1  <=>  sat(y) == y (NaN: sat gives 0, the compare fails; -0 passes): one FADD.SAT on the FMA pipe
+// and one compare instead of two compares and a predicate merge on the half-rate ALU pipe
+__device__ __forceinline__ float mask01(float y, float g) { return (__saturatef(y) == y) ? g : 0.f; }
 
 __device__ __forceinline__ float lum_isp(float r, float g, float b) {  // isp/filters.py:12-14
     return (0.27f * r + 0.67f * g) + 0.06f * b;
@@ -267,13 +276,15 @@ __device__ __forceinline__ void fwd_step(int op, const float* __restrict__ c, fl
 template <int OP>
 struct PwBwd;
 
+// CLIP: 0 = no clip after the step (Filter.run), 1 = clip, the body masks the upstream gradient with the
+// step's own output, 2 = clip, the caller has masked the gradient already (compile-time sequences)
 #define AISP_MASK_CLIP(yr, yg, yb)                                   \
-    if (CLIP) { gr = mask01(yr, gr); gg = mask01(yg, gg); gb = mask01(yb, gb); }
+    if (CLIP == 1) { gr = mask01(yr, gr); gg = mask01(yg, gg); gb = mask01(yb, gb); }
 
 template <>
 struct PwBwd<AISP_OP_EXPOSURE> {
     static constexpr int NACC = 1;
-    template <bool GIMG, bool CLIP>
+    template <bool GIMG, int CLIP>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
                                               float& gb, float* acc) {
         const float s = c[0];
@@ -286,7 +297,7 @@ struct PwBwd<AISP_OP_EXPOSURE> {
 template <>
 struct PwBwd<AISP_OP_GAMMA> {
     static constexpr int NACC = 1;
-    template <bool GIMG, bool CLIP>
+    template <bool GIMG, int CLIP>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
                                               float& gb, float* acc) {
         const float p = c[0];
@@ -294,11 +305,12 @@ struct PwBwd<AISP_OP_GAMMA> {
         const float lr = lg2_mufu(xr), lg = lg2_mufu(xg), lb = lg2_mufu(xb);
         const float yr = ex2_mufu(p * lr), yg = ex2_mufu(p * lg), yb = ex2_mufu(p * lb);
         AISP_MASK_CLIP(yr, yg, yb)
-        acc[0] = fmaf(gr * yr, lr, fmaf(gg * yg, lg, fmaf(gb * yb, lb, acc[0])));  // x ln2 in finalize
-        if (GIMG) {  // p * x^(p-1), only where the min-clamp passed (x >= 0.001, inclusive)
-            gr = (r >= 0.001f) ? gr * p * __fdividef(yr, xr) : 0.f;
-            gg = (g >= 0.001f) ? gg * p * __fdividef(yg, xg) : 0.f;
-            gb = (b >= 0.001f) ? gb * p * __fdividef(yb, xb) : 0.f;
+        const float tr = gr * yr, tg = gg * yg, tb = gb * yb;
+        acc[0] = fmaf(tr, lr, fmaf(tg, lg, fmaf(tb, lb, acc[0])));  // x ln2 in finalize
+        if (GIMG) {  // g * p * x^(p-1) = (g * y) * (p / x), only where the min-clamp passed (x >= 0.001, inclusive)
+            gr = (r >= 0.001f) ? tr * (p * rcp_mufu(xr)) : 0.f;
+            gg = (g >= 0.001f) ? tg * (p * rcp_mufu(xg)) : 0.f;
+            gb = (b >= 0.001f) ? tb * (p * rcp_mufu(xb)) : 0.f;
         }
     }
 };
@@ -306,7 +318,7 @@ struct PwBwd<AISP_OP_GAMMA> {
 template <>
 struct PwBwd<AISP_OP_WB> {
     static constexpr int NACC = 3;
-    template <bool GIMG, bool CLIP>
+    template <bool GIMG, int CLIP>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
                                               float& gb, float* acc) {
         AISP_MASK_CLIP(r * c[0], g * c[1], b * c[2])
@@ -318,7 +330,7 @@ struct PwBwd<AISP_OP_WB> {
 template <>
 struct PwBwd<AISP_OP_CCM> {
     static constexpr int NACC = 9;
-    template <bool GIMG, bool CLIP>
+    template <bool GIMG, int CLIP>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
                                               float& gb, float* acc) {
         const float yr = (r * c[0] + g * c[1]) + b * c[2];
@@ -329,9 +341,9 @@ struct PwBwd<AISP_OP_CCM> {
         acc[3] = fmaf(gg, r, acc[3]); acc[4] = fmaf(gg, g, acc[4]); acc[5] = fmaf(gg, b, acc[5]);
         acc[6] = fmaf(gb, r, acc[6]); acc[7] = fmaf(gb, g, acc[7]); acc[8] = fmaf(gb, b, acc[8]);
         if (GIMG) {  // M^T gy
-            const float xr = c[0] * gr + c[3] * gg + c[6] * gb;
-            const float xg = c[1] * gr + c[4] * gg + c[7] * gb;
-            const float xb = c[2] * gr + c[5] * gg + c[8] * gb;
+            const float xr = fmaf(c[6], gb, fmaf(c[3], gg, c[0] * gr));
+            const float xg = fmaf(c[7], gb, fmaf(c[4], gg, c[1] * gr));
+            const float xb = fmaf(c[8], gb, fmaf(c[5], gg, c[2] * gr));
             gr = xr; gg = xg; gb = xb;
         }
     }
@@ -339,7 +351,7 @@ struct PwBwd<AISP_OP_CCM> {
 
 // one channel of a curve filter.  u_k = sat(8x - k) = 8 * clip(x - k/8, 0, 1/8) (see curve8);
 // accumulates g*u_k (8x the segment sums, undone in finalize_grads) and g*y.
-template <bool GIMG, bool CLIP>
+template <bool GIMG, int CLIP>
 __device__ __forceinline__ void curve8_bwd(float x, const float* c, int stride, float sc, float& g,
                                            float* acc, int astride, float& yacc) {
     float u[8], v[8];
@@ -351,7 +363,7 @@ __device__ __forceinline__ void curve8_bwd(float x, const float* c, int stride, 
         sum = fmaf(u[k], c[k * stride], sum);
     }
     const float y = sum * (sc * 0.125f);
-    if (CLIP) g = mask01(y, g);
+    if (CLIP == 1) g = mask01(y, g);
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k * astride] = fmaf(g, u[k], acc[k * astride]);
     yacc = fmaf(g, y, yacc);
@@ -366,7 +378,7 @@ __device__ __forceinline__ void curve8_bwd(float x, const float* c, int stride, 
 template <>
 struct PwBwd<AISP_OP_TONE> {
     static constexpr int NACC = 9;
-    template <bool GIMG, bool CLIP>
+    template <bool GIMG, int CLIP>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
                                               float& gb, float* acc) {
         curve8_bwd<GIMG, CLIP>(r, c, 1, c[8], gr, acc, 1, acc[8]);
@@ -378,7 +390,7 @@ struct PwBwd<AISP_OP_TONE> {
 template <>
 struct PwBwd<AISP_OP_COLOR> {
     static constexpr int NACC = 27;
-    template <bool GIMG, bool CLIP>
+    template <bool GIMG, int CLIP>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
                                               float& gb, float* acc) {
         curve8_bwd<GIMG, CLIP>(r, c + 0, 3, c[24], gr, acc + 0, 3, acc[24]);
@@ -390,7 +402,7 @@ struct PwBwd<AISP_OP_COLOR> {
 template <>
 struct PwBwd<AISP_OP_CONTRAST> {
     static constexpr int NACC = 1;
-    template <bool GIMG, bool CLIP>
+    template <bool GIMG, int CLIP>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
                                               float& gb, float* acc) {
         const float p = c[0], ip = 1.f - p;
@@ -419,7 +431,7 @@ struct PwBwd<AISP_OP_CONTRAST> {
 template <>
 struct PwBwd<AISP_OP_WNB> {
     static constexpr int NACC = 1;
-    template <bool GIMG, bool CLIP>
+    template <bool GIMG, int CLIP>
     static __device__ __forceinline__ void px(const float* c, float r, float g, float b, float& gr, float& gg,
                                               float& gb, float* acc) {
         const float p = c[0], ip = 1.f - p;
@@ -438,7 +450,7 @@ struct PwBwd<AISP_OP_WNB> {
 template <>
 struct PwBwd<AISP_OP_SATPLUS> {
     static constexpr int NACC = 1;
-    template <bool GIMG, bool CLIP>
+    template <bool GIMG, int CLIP>
     static __device__ __forceinline__ void px(const float* c, float r0, float g0, float b0, float& gr, float& gg,
                                               float& gb, float* acc) {
         const float p = c[0], ip = 1.f - p;

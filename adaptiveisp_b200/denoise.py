@@ -7,7 +7,8 @@ Both are built for the one window configuration the reference uses, ``search_win
 (the kernel's tile geometry is that of an 11x11 search and a 5x5 patch); other sizes raise.  Gradients:
 w.r.t. ``h`` (closed form accumulated in the forward pass, as for the filter); an image that requires grad
 raises -- use ``DenoiseFilter`` for that.  ``NonLocalMeansParam`` (:122-157, the unfold / reflect-pad
-variant with a learnable scalar, used nowhere in the reference) is not built.
+variant with a learnable scalar ``h``, used nowhere in the reference) runs on a plain, untuned kernel
+(``aisp_nlm_param_fwd``) for any odd window.
 
 ``rgb_to_luminance`` / ``ShiftStack`` / ``BoxFilter`` are the reference's small PyTorch helpers, kept for
 API completeness (plain torch ops, not on any hot path).
@@ -137,9 +138,46 @@ class NonLocalMeans(_NlmBase):
     GRAY = False
 
 
-class NonLocalMeansParam(nn.Module):
-    """isp/denoise.py:122-157 -- used nowhere in the reference; not built."""
+class _NlmParam(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb, h, window: int):
+        _lib.require_image(rgb, "rgb")
+        if ctx.needs_input_grad[0]:
+            raise _lib.AispError("NonLocalMeansParam differentiates w.r.t. h only")
+        B, _, H, W = rgb.shape
+        luma = rgb_to_luminance(rgb).contiguous()
+        out = torch.empty_like(rgb)
+        stash = torch.empty_like(rgb) if ctx.needs_input_grad[1] else None
+        hd = h.detach().reshape(-1)[:1].to(torch.float32).contiguous()
+        with torch.cuda.device(rgb.device):
+            rc = _lib.lib().aisp_nlm_param_fwd(rgb.data_ptr(), luma.data_ptr(), out.data_ptr(), _lib.ptr(stash),
+                                               hd.data_ptr(), B, H, W, int(window), _lib.stream_ptr(rgb.device))
+        _lib.check(rc, "aisp_nlm_param_fwd")
+        ctx.save_for_backward(stash)
+        ctx.h_shape = h.shape
+        return out
 
-    def __init__(self, *args, **kwargs):
+    @staticmethod
+    def backward(ctx, g):
+        (stash,) = ctx.saved_tensors
+        if stash is None:
+            return None, None, None
+        return None, (g * stash).sum().reshape(ctx.h_shape), None
+
+
+class NonLocalMeansParam(nn.Module):
+    """isp/denoise.py:122-157: reflect-padded search window, patch box as large as the search window
+    (:145-146), one learnable scalar ``h`` (``nn.Parameter`` of shape [1], as in the reference)."""
+
+    def __init__(self, h0, search_window_size=21, patch_size=7):
         super().__init__()
-        raise NotImplementedError("NonLocalMeansParam is instantiated nowhere in the reference and is not built")
+        if search_window_size % 2 != 1:
+            raise _lib.AispError("search_window_size must be odd")
+        self.h = nn.Parameter(torch.tensor([float(h0)]), requires_grad=True)
+        self.box_sum = BoxFilter(window_size=patch_size, reduction="sum")   # kept for parity; unused by forward (as in the reference)
+        self.r = search_window_size // 2
+        self.gen_window_stack = ShiftStack(window_size=search_window_size)
+        self.search_window_size = search_window_size
+
+    def forward(self, rgb):
+        return _NlmParam.apply(rgb, self.h, self.search_window_size)

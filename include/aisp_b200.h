@@ -178,6 +178,16 @@ int aisp_nlm_fwd(const float* img, float* out, const float* params, const int32_
 int aisp_nlm_module_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H, int W,
                         float* dout_dh, int gray, void* stream);
 
+/*
+ * NonLocalMeansParam.forward(rgb) of isp/denoise.py:122-157: reflect-padded search window `window` (odd,
+ * window / 2 < min(H, W)), patch box as large as the search window (:145-146), ONE scalar h for the whole
+ * batch (`h`: device pointer to one float, the module's nn.Parameter).  luma [B,H,W] = rgb_to_luminance(rgb)
+ * (isp/denoise.py:11-17).  dout_dh [B,3,H,W] or NULL: d out / d h per element; grad_h = sum(grad_out * dout_dh).
+ * Instantiated nowhere in the reference: a plain one-pixel-per-thread kernel, not a tuned one.
+ */
+int aisp_nlm_param_fwd(const float* rgb, const float* luma, float* out, float* dout_dh, const float* h, int B, int H,
+                       int W, int window, void* stream);
+
 /* Backward of NLM w.r.t. h:  grad_params[b,0] = sum_{c,y,x} grad_out * dout_dh. */
 int aisp_nlm_bwd(const float* grad_out, const float* dout_dh, const int32_t* ops, int B, int H, int W,
                  float* grad_params, void* scratch, size_t scratch_bytes, void* stream);

@@ -375,6 +375,31 @@ def nlm_rgb_module(rgb, h, search: int = 11, patch: int = 5):
     return torch.clamp(acc / wsum, 0.0, 1.0)
 
 
+def nlm_param_module(rgb, h, search: int = 21):
+    """``NonLocalMeansParam(h0, search).forward(rgb)`` of isp/denoise.py:122-157, shift by shift instead of
+    through the unfolded window stacks: the luma and the image are padded by reflection (:133-137), the
+    squared luma differences are formed at the unpadded positions (:142), padded by reflection again
+    (:144) and box-summed over a window as large as the SEARCH window (:145-146); one scalar ``h``."""
+    import torch.nn.functional as F
+    r = (search - 1) // 2
+    B, _, H, W = rgb.shape
+    y = lum_nlm(torch.clip(rgb, 0.0, 1.0))
+    pad = [r, r, r, r]
+    y_pad = F.pad(y, pad=pad, mode="reflect")
+    rgb_pad = F.pad(rgb, pad=pad, mode="reflect")
+    hh = torch.relu(h) + 1e-8
+    acc = torch.zeros_like(rgb)
+    wsum = torch.zeros_like(y)
+    for wy in range(search):            # window index = wy * search + wx (unfold order)
+        for wx in range(search):
+            dis = (y - y_pad[:, :, wy:wy + H, wx:wx + W]) ** 2
+            box = F.avg_pool2d(F.pad(dis, pad=pad, mode="reflect"), search, stride=1) * float(search * search)
+            w = torch.exp(-torch.sqrt(torch.relu(box)) / hh)
+            acc = acc + w * rgb_pad[:, :, wy:wy + H, wx:wx + W]
+            wsum = wsum + w
+    return torch.clamp(acc / wsum, 0.0, 1.0)
+
+
 # ----------------------------------------------------------------------------------------------
 # dispatch + Filter.forward / Filter.run wrappers
 # ----------------------------------------------------------------------------------------------

@@ -23,6 +23,15 @@ for what in "$@"; do
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:nlm2_kernel -s 3 -c 1 -f -o $OUT/prof_nlm2_${TAG} \
           python scripts/micro/nlm_ab.py > $OUT/${TAG}_ncu_nlm.log 2>&1
       tail -3 $OUT/${TAG}_ncu_nlm.log;;
+    chain)
+      timeout 600 python scripts/micro/chain_bench.py 2>&1 | tee $OUT/${TAG}_chain.jsonl;;
+    chain_ab)
+      AISP_CHAIN_MINB=3 timeout 600 python scripts/micro/chain_bench.py --cases 1 2>&1 | tee $OUT/${TAG}_chain_ab.jsonl
+      timeout 600 python scripts/micro/chain_bench.py --cases 1 2>&1 | tee -a $OUT/${TAG}_chain_ab.jsonl;;
+    ncu_chain)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:pw_chain_fixed -s 4 -c 1 -f -o $OUT/prof_chainfixed_${TAG} \
+          python scripts/micro/chain_bench.py --iters 2 > $OUT/${TAG}_ncu_chain.log 2>&1
+      tail -3 $OUT/${TAG}_ncu_chain.log;;
     *) echo "unknown step $what";;
   esac
 done

@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--cases", type=int, default=0, help="only the first N cases (0: all)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     L = _lib.lib()
@@ -81,6 +82,8 @@ def main():
         ("T_C", [AF.OP_TONE, AF.OP_COLOR]),
     ]
     npx = B * H * W
+    if args.cases:
+        cases = cases[:args.cases]
     for name, seq in cases:
         S = len(seq)
         P = params(seq)

@@ -211,6 +211,23 @@ def denoise_modules_golden(ref):
     return out
 
 
+def denoise_param_golden(ref):
+    """NonLocalMeansParam (isp/denoise.py:122-157; instantiated nowhere in the reference): reflect-padded
+    windows of 5 and 7 on small images that spill outside [0,1], output and the gradient of the scalar h."""
+    out = {}
+    for variant, (B, H, W, S, h0, seed) in {"a": (2, 14, 17, 5, 0.35, 50), "b": (1, 19, 16, 7, 0.2, 51)}.items():
+        img = cases.edge_image(B, H, W, seed)
+        g = cases.grad_out(img.shape, seed).abs()
+        mod = ref.denoise.NonLocalMeansParam(h0, search_window_size=S)
+        y = mod(img)
+        (y * g).sum().backward()
+        key = f"param.{variant}"
+        out[key + ".img"], out[key + ".g"] = img.numpy(), g.numpy()
+        out[key + ".cfg"] = np.array([S, h0], dtype=np.float64)
+        out[key + ".out"], out[key + ".gh"] = y.detach().numpy(), mod.h.grad.numpy()
+    return out
+
+
 def main():
     ref = ref_shim.load()
     a = agent_golden(ref)
@@ -222,6 +239,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "select.npz"), **s)
     d = denoise_modules_golden(ref)
     np.savez_compressed(os.path.join(HERE, "denoise_modules.npz"), **d)
+    np.savez_compressed(os.path.join(HERE, "denoise_param.npz"), **denoise_param_golden(ref))
     for fn in ("filters.npz", "select.npz"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")
 

@@ -801,12 +801,43 @@ def test_bare_nlm_modules_match_reference_vectors(dev, name, variant):
     assert_grad(h.grad.cpu().numpy(), G[key + ".gh"], 2e-4, f"{name} d/dh")   # the reference's own fp32 noise is ~5e-5
 
 
+@pytest.mark.parametrize("variant", ["a", "b"])
+def test_nlm_param_module_matches_reference_vectors(dev, variant):
+    """adaptiveisp_b200.denoise.NonLocalMeansParam (isp/denoise.py:122-157: reflect-padded search window, box
+    as large as the window, one learnable scalar h) against vectors from the unmodified reference, and against
+    the oracle on a larger image with the default-style window."""
+    import os
+    from adaptiveisp_b200 import denoise as D
+    G = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "denoise_param.npz")))
+    key = f"param.{variant}"
+    img, g = torch.from_numpy(G[key + ".img"]).to(dev), torch.from_numpy(G[key + ".g"]).to(dev)
+    S, h0 = int(G[key + ".cfg"][0]), float(G[key + ".cfg"][1])
+    mod = D.NonLocalMeansParam(h0, search_window_size=S).to(dev)
+    assert [k for k, _ in mod.named_parameters()] == ["h"] and mod.h.shape == (1,)
+    y = mod(img)
+    (y * g).sum().backward()
+    assert out_err(y.detach().cpu().numpy(), G[key + ".out"]) <= OUT_ATOL
+    assert_grad(mod.h.grad.cpu().numpy(), G[key + ".gh"], 2e-4, "param d/dh")
+    if variant == "a":   # a larger, ragged image against the oracle
+        x = cases.edge_image(2, 37, 45, seed=52)
+        hc = torch.tensor([0.3], requires_grad=True)
+        yc = O.nlm_param_module(x, hc, 9)
+        yc.sum().backward()
+        m2 = D.NonLocalMeansParam(0.3, search_window_size=9).to(dev)
+        y2 = m2(x.to(dev))
+        y2.sum().backward()
+        assert out_err(y2.detach().cpu().numpy(), yc.detach().numpy()) <= OUT_ATOL
+        assert_grad(m2.h.grad.cpu().numpy(), hc.grad.numpy(), 2e-4, "param d/dh (oracle)")
+
+
 def test_bare_nlm_modules_api(dev):
     from adaptiveisp_b200 import AispError, denoise as D
     with pytest.raises(AispError):
         D.NonLocalMeansGray(search_window_size=21, patch_size=7)       # only the 11 / 5 configuration is built
-    with pytest.raises(NotImplementedError):
-        D.NonLocalMeansParam(0.5)
+    with pytest.raises(AispError):
+        D.NonLocalMeansParam(0.5, search_window_size=4)                # windows are odd
+    with pytest.raises(AispError):
+        D.NonLocalMeansParam(0.5, search_window_size=21).to(dev)(cases.lod_batch(1, 8, 64, seed=1, device=dev))   # pad >= H
     x = cases.lod_batch(2, 48, 64, seed=3, device=dev)
     # scalar h shared by the batch: the gradient is summed over the samples
     h = torch.tensor([0.3], device=dev, requires_grad=True)
