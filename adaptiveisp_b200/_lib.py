@@ -38,6 +38,8 @@ SIGNATURES = {
     "aisp_sharpen_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "aisp_nlm_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "aisp_nlm_module_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P]),
+    "aisp_shot_read_noise": (c_int, [_P, _P, _P, _P, _P, _P, c_int, ctypes.c_longlong, ctypes.c_ulonglong,
+                                     ctypes.c_ulonglong, _P]),
     "aisp_nlm_param_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "aisp_nlm_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "aisp_nlm_bwd_img": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),

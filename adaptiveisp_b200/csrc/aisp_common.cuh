@@ -109,6 +109,21 @@ inline cudaError_t launch_pdl_smem(void (*kernel)(KArgs...), dim3 grid, dim3 blo
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// cp.async (LDGSTS) with zero-fill: global -> shared without staging registers
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int n = valid ? 16 : 0;   // src-size 0: nothing is read, the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill(void* smem, const void* gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int n = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // torch.clip semantics: NaN stays NaN (fminf/fmaxf would swallow it)
 __device__ __forceinline__ float clip01(float y) {
     // two NaN-propagating FMNMX instead of two compare+select pairs

@@ -38,6 +38,8 @@ cudaError_t launch_regress(const float*, const int32_t*, const int32_t*, int, in
 cudaError_t launch_value_stats(const float*, int, int, float*, cudaStream_t);
 cudaError_t launch_nlm_module_fwd(const float*, float*, const float*, const int32_t*, int, int, int, float*, int, cudaStream_t);
 cudaError_t launch_nlm_param_fwd(const float*, const float*, float*, float*, const float*, int, int, int, int, cudaStream_t);
+cudaError_t launch_shot_read_noise(const float*, const float*, float*, const float*, const float*, const float*, int,
+                                   long long, unsigned long long, unsigned long long, cudaStream_t);
 bool pointwise_can_emit(int, int, int, int);
 bool sharpen_can_emit(int, int, int, int);
 int chain_bwd_max_steps();
@@ -185,6 +187,14 @@ int aisp_block_mean(const float* img, float* down, int B, int H, int W, int out_
     if (!shape_ok(B, H, W) || out_h <= 0 || out_w <= 0 || (long long)B * 3 > 65535) return AISP_ERR_SHAPE;
     if (H % out_h != 0 || W % out_w != 0) return AISP_ERR_UNSUPPORTED;  // adaptive pooling with uneven windows
     return (int)launch_block_mean(img, down, B, H, W, out_h, out_w, (cudaStream_t)stream);
+}
+
+int aisp_shot_read_noise(const float* img, const float* z, float* out, const float* shot, const float* read,
+                         const float* gain, int B, long long n_per_image, unsigned long long seed,
+                         unsigned long long offset, void* stream) {
+    if (!img || !out || !shot || !read) return AISP_ERR_NULL;
+    if (B <= 0 || B > 65535 || n_per_image <= 0) return AISP_ERR_SHAPE;
+    return (int)launch_shot_read_noise(img, z, out, shot, read, gain, B, n_per_image, seed, offset, (cudaStream_t)stream);
 }
 
 int aisp_value_stats(const float* down, int B, int h, int w, float* stats, void* stream) {

@@ -20,7 +20,6 @@
 // instantiation with 27-wide accumulators launched with ONE CTA per sample (it walks the sample's
 // chunks); the main instantiation skips those samples and vice versa, so ColorFilter costs the common
 // sequences nothing.
-#include <cstdlib>
 #include "pointwise_math.cuh"
 
 namespace aisp {
@@ -28,20 +27,6 @@ namespace aisp {
 constexpr int kChainMax = AISP_MAX_CHAIN_BWD;   // longest sequence differentiated in one pass
 constexpr int kChainPx = 4;                     // pixels per thread per round
 constexpr int kRoundPx = kThreads * kChainPx;   // 1024 pixels per CTA round
-
-__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    const int n = valid ? 16 : 0;   // src-size 0: nothing is read, the 16 bytes are zero-filled
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async4_zfill(void* smem, const void* gmem, bool valid) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    const int n = valid ? 4 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __host__ __device__ __forceinline__ int op_nacc(int op) {
     switch (op) {
@@ -171,7 +156,6 @@ __device__ __forceinline__ bool owned_by_fixed(const int32_t* __restrict__ o, in
 __device__ __forceinline__ float clip_next(float y) { return fmaf(0.f, y, __saturatef(y)); }
 
 // reverse sweep from stage K down to stage 0 (compile-time recursion: the op is a template argument)
-constexpr int kFixedPx = 2;   // pixels a thread carries through forward + reverse sweep at a time (half a ring vector)
 // clamp mask of a stage output as an all-ones / all-zeros word, taken in the forward sweep and ANDed onto the
 // gradient in the reverse sweep: a value in a register, not a predicate that has to survive the sweep
 // (inline PTX: written in C the compiler turns the word back into a predicate and then packs 18 of them into
@@ -187,7 +171,7 @@ __device__ __forceinline__ float and_bits(float g, unsigned m) {
     return r;
 }
 
-template <typename SEQ, int K, bool GIMG, bool CLIP>
+template <typename SEQ, int K, bool GIMG, bool CLIP, int kFixedPx>
 __device__ __forceinline__ void fixed_reverse(const float (*sc)[kConst], const float (&X)[SEQ::N][3][kFixedPx],
                                               const unsigned (&M)[SEQ::N][3][kFixedPx], float (&gr)[kFixedPx],
                                               float (&gg)[kFixedPx], float (&gb)[kFixedPx], float (&acc)[SEQ::N][9]) {
@@ -199,10 +183,10 @@ __device__ __forceinline__ void fixed_reverse(const float (*sc)[kConst], const f
         PwBwd<SEQ::at(K)>::template px<(K > 0) || GIMG, MODE>(sc[K], X[K][0][v], X[K][1][v], X[K][2][v], gr[v], gg[v], gb[v],
                                                               acc[K]);
     }
-    if constexpr (K > 0) fixed_reverse<SEQ, K - 1, GIMG, CLIP>(sc, X, M, gr, gg, gb, acc);
+    if constexpr (K > 0) fixed_reverse<SEQ, K - 1, GIMG, CLIP, kFixedPx>(sc, X, M, gr, gg, gb, acc);
 }
 
-template <int VEC, bool GIMG, bool CLIP, typename SEQ, int MINB>
+template <int VEC, bool GIMG, bool CLIP, typename SEQ, int MINB, int kFixedPx>
 __global__ void __launch_bounds__(kThreads, MINB)
 pw_chain_fixed_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gout, const float* __restrict__ params,
                           const int32_t* __restrict__ ops, const int32_t* __restrict__ seq_len, int N, int S, int flags,
@@ -273,7 +257,7 @@ pw_chain_fixed_bwd_kernel(const float* __restrict__ img, const float* __restrict
             cp_async_wait<1>();
             const int i = chunk0 + (r * kThreads + tid) * kChainPx;
             if (i >= N) continue;
-            const float2* slot = reinterpret_cast<const float2*>(ring + (size_t)(r & 1) * 6 * kThreads + tid);
+            const float* slot = reinterpret_cast<const float*>(ring + (size_t)(r & 1) * 6 * kThreads + tid);
             // the four pixels of the ring vector go through forward + reverse sweep two at a time: half the
             // live stage inputs, and the loop body (not unrolled) is half the code
 #pragma unroll 1
@@ -283,12 +267,17 @@ pw_chain_fixed_bwd_kernel(const float* __restrict__ img, const float* __restrict
                 unsigned M[L][3][kFixedPx];   // clamp mask of stage k's output (stages 0 .. L-2)
 #pragma unroll
                 for (int pl = 0; pl < 3; ++pl) {
-                    const float2 a = slot[2 * pl * kThreads + hv];
-                    X[0][pl][0] = a.x; X[0][pl][1] = a.y;
+                    if (kFixedPx == 2) {
+                        const float2 a = *reinterpret_cast<const float2*>(slot + 4 * pl * kThreads + 2 * hv);
+                        X[0][pl][0] = a.x; X[0][pl][kFixedPx - 1] = a.y;
+                    } else {
+                        X[0][pl][0] = slot[4 * pl * kThreads + hv];
+                    }
                 }
-                if (VEC == 1) {   // ragged tail: pixels past the end repeat a real pixel (and get a zero gradient below)
-                    if (i2 >= N) { X[0][0][0] = 0.5f; X[0][1][0] = 0.5f; X[0][2][0] = 0.5f; }
-                    if (i2 + 1 >= N) { X[0][0][1] = X[0][0][0]; X[0][1][1] = X[0][1][0]; X[0][2][1] = X[0][2][0]; }
+                if (VEC == 1) {   // ragged tail: pixels past the end hold a harmless value (and get a zero gradient below)
+#pragma unroll
+                    for (int v = 0; v < kFixedPx; ++v)
+                        if (i2 + v >= N) { X[0][0][v] = 0.5f; X[0][1][v] = 0.5f; X[0][2][v] = 0.5f; }
                 }
 #pragma unroll
                 for (int k = 0; k + 1 < L; ++k) {
@@ -303,23 +292,29 @@ pw_chain_fixed_bwd_kernel(const float* __restrict__ img, const float* __restrict
                     }
                 }
                 float gr[kFixedPx], gg[kFixedPx], gb[kFixedPx];
-                {
-                    const float2 a = slot[2 * 3 * kThreads + hv], c = slot[2 * 4 * kThreads + hv], d = slot[2 * 5 * kThreads + hv];
-                    gr[0] = a.x; gr[1] = a.y;
-                    gg[0] = c.x; gg[1] = c.y;
-                    gb[0] = d.x; gb[1] = d.y;
+                if (kFixedPx == 2) {
+                    const float2 a = *reinterpret_cast<const float2*>(slot + 4 * 3 * kThreads + 2 * hv);
+                    const float2 c = *reinterpret_cast<const float2*>(slot + 4 * 4 * kThreads + 2 * hv);
+                    const float2 d = *reinterpret_cast<const float2*>(slot + 4 * 5 * kThreads + 2 * hv);
+                    gr[0] = a.x; gr[kFixedPx - 1] = a.y;
+                    gg[0] = c.x; gg[kFixedPx - 1] = c.y;
+                    gb[0] = d.x; gb[kFixedPx - 1] = d.y;
+                } else {
+                    gr[0] = slot[4 * 3 * kThreads + hv];
+                    gg[0] = slot[4 * 4 * kThreads + hv];
+                    gb[0] = slot[4 * 5 * kThreads + hv];
                 }
                 if (VEC == 1) {
 #pragma unroll
                     for (int v = 0; v < kFixedPx; ++v)
                         if (i2 + v >= N) { gr[v] = 0.f; gg[v] = 0.f; gb[v] = 0.f; }
                 }
-                fixed_reverse<SEQ, L - 1, GIMG, CLIP>(sc, X, M, gr, gg, gb, acc);
+                fixed_reverse<SEQ, L - 1, GIMG, CLIP, kFixedPx>(sc, X, M, gr, gg, gb, acc);
                 if (GIMG) {
-                    if (VEC == 4) {
-                        *reinterpret_cast<float2*>(gi + i2) = make_float2(gr[0], gr[1]);
-                        *reinterpret_cast<float2*>(gi + N + i2) = make_float2(gg[0], gg[1]);
-                        *reinterpret_cast<float2*>(gi + 2 * (size_t)N + i2) = make_float2(gb[0], gb[1]);
+                    if (VEC == 4 && kFixedPx == 2) {
+                        *reinterpret_cast<float2*>(gi + i2) = make_float2(gr[0], gr[kFixedPx - 1]);
+                        *reinterpret_cast<float2*>(gi + N + i2) = make_float2(gg[0], gg[kFixedPx - 1]);
+                        *reinterpret_cast<float2*>(gi + 2 * (size_t)N + i2) = make_float2(gb[0], gb[kFixedPx - 1]);
                     } else {
 #pragma unroll
                         for (int v = 0; v < kFixedPx; ++v)
@@ -577,12 +572,12 @@ static cudaError_t launch_one(dim3 grid, cudaStream_t st, const float* img, cons
     return cudaGetLastError();
 }
 
-template <int VEC, bool GIMG, bool CLIP, typename SEQ, int MINB>
+template <int VEC, bool GIMG, bool CLIP, typename SEQ, int MINB, int FPX>
 static cudaError_t launch_fixed(dim3 grid, cudaStream_t st, const float* img, const float* gout, const float* params,
                                 const int32_t* ops, const int32_t* seq_len, int N, int S, int flags, int rounds,
                                 int nchunks, float* gimg, float* partial) {
     constexpr size_t smem = (size_t)(2 * 6) * kThreads * sizeof(float4);
-    auto kern = pw_chain_fixed_bwd_kernel<VEC, GIMG, CLIP, SEQ, MINB>;
+    auto kern = pw_chain_fixed_bwd_kernel<VEC, GIMG, CLIP, SEQ, MINB, FPX>;
     static bool attr_set_on[64] = {};
     int devi = 0;
     cudaGetDevice(&devi);
@@ -640,12 +635,10 @@ cudaError_t launch_pointwise_chain_bwd(const float* img, const float* gout, cons
     if (e != cudaSuccess) return e;
     // compile-time sequences (samples the generic kernel skipped)
     if (S >= SeqEGWC::N) {
-        static const bool minb3 = [] { const char* e = getenv("AISP_CHAIN_MINB"); return e && e[0] == '3'; }();
-#define AISP_LAUNCH_FIXED(VEC, GIMG, CLIP)                                                                              \
-    (minb3 ? launch_fixed<VEC, GIMG, CLIP, SeqEGWC, 3>(grid, st, img, gout, params, ops, seq_len, (int)N, S, flags, rounds, \
-                                                       nchunks, grad_img, partial)                                      \
-           : launch_fixed<VEC, GIMG, CLIP, SeqEGWC, 4>(grid, st, img, gout, params, ops, seq_len, (int)N, S, flags, rounds, \
-                                                       nchunks, grad_img, partial))
+        // two pixels per pass at 80 registers (3 CTAs / SM): measured best of {1, 2} pixels x {3, 4} CTAs / SM
+#define AISP_LAUNCH_FIXED(VEC, GIMG, CLIP)                                                                          \
+    launch_fixed<VEC, GIMG, CLIP, SeqEGWC, 3, 2>(grid, st, img, gout, params, ops, seq_len, (int)N, S, flags, rounds, \
+                                                 nchunks, grad_img, partial)
         const bool clip = (flags & AISP_SEQ_CLIP) != 0;
         if (vec) {
             if (grad_img) e = clip ? AISP_LAUNCH_FIXED(4, true, true) : AISP_LAUNCH_FIXED(4, true, false);

@@ -52,34 +52,48 @@ def bench_config(world):
 
 
 # per-launch DRAM traffic measured by ncu (--set full) at this workload, profiles/r01_ncu_summary.txt
-NCU_TRAFFIC_BYTES = {"NLM": 550.5e6, "pw_fwd": 352.9e6, "pw_bwd": 410.6e6, "sharpen_fwd": 355.2e6, "sharpen_bwd": 407.2e6}
-# SASS instructions per (pixel, shift) of nlm_kernel<grad>'s main loop (993 per 44, cuobjdump) and lane use
-NLM_INSTR_PER_PXSHIFT, NLM_LANE_EFF = 959.0 / 44.0, 28.0 / 32.0
+NCU_TRAFFIC_BYTES = {"NLM": 553.2e6, "pw_fwd": 352.9e6, "pw_bwd": 410.6e6, "sharpen_fwd": 355.2e6, "sharpen_bwd": 407.2e6}
+# nlm2_kernel<grad> (two columns per lane): SASS instructions of one dx iteration of the main loop (738,
+# cuobjdump) cover 11 dy x 4 pixels of a thread; FMA-pipe cycles of the same iteration per warp (packed
+# f32x2 instructions occupy the pipe for two cycles): 11 x (17 FFMA2 + 10 FADD2 + 5 FMUL2) x 2 + 11 x 10 FADD;
+# 30 of 32 lanes produce outputs, 60-column tiles
+NLM_INSTR_PER_PXSHIFT, NLM_FMA_CYCLES_PER_PXSHIFT = 738.0 / 44.0, (11 * (32 * 2 + 10)) / 44.0
+
+
+def nlm_lane_eff(W):
+    tiles = (W + 59) // 60
+    return (30.0 / 32.0) * W / (tiles * 60.0)
 
 
 def nlm_active_fraction(img):
-    """Fraction of the kernel's 4-row warp groups that run the 121-shift loop: a group whose whole footprint
-    (rows r0-7 .. r0+10, circular) is exactly zero takes the zero shortcut."""
+    """Fraction of the kernel's 2-row warp groups that run the 121-shift loop: a group whose whole footprint
+    (rows r0-7 .. r0+8, circular) is exactly zero takes the zero shortcut."""
     Hh = img.shape[2]
     rownz = (img.abs().amax(dim=(1, 3)) > 0)                      # [B,H]
-    live = torch.zeros((img.shape[0], Hh // 4), dtype=torch.bool, device=img.device)
-    for d in range(-7, 11):
-        live |= torch.roll(rownz, shifts=-d, dims=1)[:, 0:Hh - Hh % 4:4]
+    live = torch.zeros((img.shape[0], Hh // 2), dtype=torch.bool, device=img.device)
+    for d in range(-7, 9):
+        live |= torch.roll(rownz, shifts=-d, dims=1)[:, 0:Hh - Hh % 2:2]
     return float(live.float().mean())
 
 
-def nlm_issue_bound(fwd_ms, npx, sm_mhz, active=1.0):
-    """NLM against the bound that actually limits it: warp-instruction issue (4 per clock per SM)."""
+def nlm_issue_bound(fwd_ms, npx, sm_mhz, active=1.0, W=512):
+    """NLM against the bounds that actually limit it: the FP32 pipe (128 lanes per SM and clock; a packed
+    instruction holds it for two cycles), warp-instruction issue (4 per clock per SM) and the MUFU pipe."""
     npx = npx * active
-    thread_instr = npx * 121 * NLM_INSTR_PER_PXSHIFT / NLM_LANE_EFF
+    eff = nlm_lane_eff(W)
+    thread_instr = npx * 121 * NLM_INSTR_PER_PXSHIFT / eff
     ideal_ms = thread_instr / (148 * 128 * sm_mhz * 1e6) * 1e3
+    fma_ms = npx * 121 * NLM_FMA_CYCLES_PER_PXSHIFT / eff / (148 * 128 * sm_mhz * 1e6) * 1e3
     # SURVEY 8(d)'s bound for this kernel: >= 121 sqrt + 121 exp per pixel on 16 MUFU lanes per SM and clock
     mufu_ms = npx * 242.0 / (148 * 16 * sm_mhz * 1e6) * 1e3
     return {"ideal_ms_at_full_issue_rate": round(ideal_ms, 3), "measured_ms": round(fwd_ms, 3),
             "frac": round(ideal_ms / fwd_ms, 3), "sm_mhz": sm_mhz,
+            "fp32_pipe_bound_ms": round(fma_ms, 3), "frac_of_fp32_pipe_bound": round(fma_ms / fwd_ms, 3),
             "mufu_bound_ms": round(mufu_ms, 3), "frac_of_mufu_bound": round(mufu_ms / fwd_ms, 3),
-            "active_pixel_fraction": round(active, 4),
-            "model": "active pixels * 121 shifts * 21.8 SASS instr / (28/32 lanes) / (148 SMs * 128 thread-instr/clk); "
+            "active_pixel_fraction": round(active, 4), "lane_efficiency": round(eff, 4),
+            "model": "active pixels * 121 shifts * 16.8 SASS instr / lane efficiency / (148 SMs * 128 thread-instr/clk); "
+                     "FP32 pipe: 18.5 lane-cycles per (pixel, shift) (packed f32x2 = 2 cycles) on 128 lanes per SM; "
+                     "lane efficiency = 30/32 output lanes * W / (60-column tiles * 60); "
                      "MUFU bound: 242 MUFU ops per active pixel / (148 SMs * 16 lanes/clk); active pixels = those whose "
                      "warp group does not take the all-zero-footprint shortcut (letterbox bars)"}
 
@@ -644,18 +658,18 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": bench_config(world),
-            "roofline": {"bound": "sm_issue" if dom["filter"] == "NLM" else "hbm", "kernel": ("nlm_kernel<grad>" if dom["filter"] == "NLM" else dom["filter"]) +
+            "roofline": {"bound": "sm_fp32_pipe" if dom["filter"] == "NLM" else "hbm", "kernel": ("nlm2_kernel<grad>" if dom["filter"] == "NLM" else dom["filter"]) +
                          (" fwd" if dom_fwd else " bwd"), "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "peak_source": peak_src,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
                          # ncu --set full capture (profiles/r01_ncu_summary.txt); NLM also writes its d/dh stash
                          "traffic": NCU_TRAFFIC_BYTES.get("NLM" if dom["filter"] == "NLM" else
                                                           ("pw_fwd" if dom_fwd else "pw_bwd")),
-                         "note": "NLM is SM-issue/FP32/MUFU-bound by construction (121 patch distances, sqrt and exp "
+                         "note": "NLM is FP32-pipe/issue/MUFU-bound by construction (121 patch distances, sqrt and exp "
                                  "per pixel), not HBM-bound: see 'issue_bound' and DESIGN.md 4.3; the HBM fractions "
                                  "of the HBM-bound kernels are in 'kernels' / 'hbm_frac_excl_nlm'",
                          "issue_bound": nlm_issue_bound(kern["NLM"][0], npx, (clocks.samples and clk_mhz(clocks)) or 1965.0,
-                                                        nlm_active_fraction(img))
+                                                        nlm_active_fraction(img), W)
                          if "NLM" in kern else None},
             "step_segments_ms": {"bank_fwd": round(seg_fwd, 4), "bank_bwd": round(seg_bwd, 4),
                                  "unbanked_per_filter_sum": round(sum(k["fwd_ms"] + k["bwd_ms"] for k in klist), 4)},

@@ -179,6 +179,18 @@ int aisp_nlm_module_fwd(const float* img, float* out, const float* params, const
                         float* dout_dh, int gray, void* stream);
 
 /*
+ * Shot / read noise of the synthetic-RAW model, isp/unprocess_np.py:131-181 (adjust_random_brightness +
+ * add_read_and_shot_noise; the per-image noise levels of random_noise_levels_log / _linear are drawn on the host):
+ *     out = gain[b] * img + sqrt(gain[b] * img * shot[b] + read[b]) * z,   z ~ N(0, 1)
+ * img / out [B, n_per_image] (in place allowed); shot, read [B] device; gain [B] device or NULL (1).
+ * z [B, n_per_image] device: the standard normals to use (the result is then a deterministic function of the
+ * inputs); NULL: generated in the kernel (Philox4x32-10 keyed by `seed`, counter = offset + element group).
+ */
+int aisp_shot_read_noise(const float* img, const float* z, float* out, const float* shot, const float* read,
+                         const float* gain, int B, long long n_per_image, unsigned long long seed,
+                         unsigned long long offset, void* stream);
+
+/*
  * NonLocalMeansParam.forward(rgb) of isp/denoise.py:122-157: reflect-padded search window `window` (odd,
  * window / 2 < min(H, W)), patch box as large as the search window (:145-146), ONE scalar h for the whole
  * batch (`h`: device pointer to one float, the module's nn.Parameter).  luma [B,H,W] = rgb_to_luminance(rgb)

@@ -400,6 +400,19 @@ def nlm_param_module(rgb, h, search: int = 21):
     return torch.clamp(acc / wsum, 0.0, 1.0)
 
 
+def shot_read_noise(image, shot, read, z, gain=None):
+    """isp/unprocess_np.py:131-138,178-181 with the standard normals ``z`` injected: brightness ratio, then
+    ``image + sqrt(image * shot + read) * z`` (what ``np.random.normal(0, sqrt(variance))`` computes from the
+    normals it draws).  numpy arrays, float64 like the reference; per-image levels broadcast from ``[B]``."""
+    import numpy as np
+    image = np.asarray(image, dtype=np.float64)
+    bshape = (image.shape[0],) + (1,) * (image.ndim - 1)
+    if gain is not None:
+        image = image * np.asarray(gain, dtype=np.float64).reshape(bshape)
+    variance = image * np.asarray(shot, dtype=np.float64).reshape(bshape) + np.asarray(read, dtype=np.float64).reshape(bshape)
+    return image + np.sqrt(variance) * np.asarray(z, dtype=np.float64)
+
+
 # ----------------------------------------------------------------------------------------------
 # dispatch + Filter.forward / Filter.run wrappers
 # ----------------------------------------------------------------------------------------------

@@ -26,8 +26,9 @@ for what in "$@"; do
     chain)
       timeout 600 python scripts/micro/chain_bench.py 2>&1 | tee $OUT/${TAG}_chain.jsonl;;
     chain_ab)
-      AISP_CHAIN_MINB=3 timeout 600 python scripts/micro/chain_bench.py --cases 1 2>&1 | tee $OUT/${TAG}_chain_ab.jsonl
-      timeout 600 python scripts/micro/chain_bench.py --cases 1 2>&1 | tee -a $OUT/${TAG}_chain_ab.jsonl;;
+      rm -f $OUT/${TAG}_chain_ab.jsonl
+      for c in 13 14 23 24; do echo "cfg $c" | tee -a $OUT/${TAG}_chain_ab.jsonl
+        AISP_CHAIN_CFG=$c timeout 600 python scripts/micro/chain_bench.py --cases 1 2>&1 | tee -a $OUT/${TAG}_chain_ab.jsonl; done;;
     ncu_chain)
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:pw_chain_fixed -s 4 -c 1 -f -o $OUT/prof_chainfixed_${TAG} \
           python scripts/micro/chain_bench.py --iters 2 > $OUT/${TAG}_ncu_chain.log 2>&1

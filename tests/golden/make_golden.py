@@ -228,6 +228,36 @@ def denoise_param_golden(ref):
     return out
 
 
+def noise_model_golden():
+    """Noise model of isp/unprocess_np.py:131-181 from the unmodified module (NumPy RNG, seeded): per-image
+    levels of random_noise_levels_log, brightness ratios of adjust_random_brightness, and
+    add_read_and_shot_noise on the scaled frames together with the standard normals it drew."""
+    import importlib.util
+    import sys
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot"):      # imported at module level for a debug viewer only
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    spec = importlib.util.spec_from_file_location("ref_unprocess", os.path.join(ref_shim.REF_ROOT, "isp", "unprocess_np.py"))
+    ru = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ru)
+    np.random.seed(21)
+    img = np.random.rand(3, 3, 10, 12).astype(np.float32)
+    np.random.seed(22)
+    levels = [ru.random_noise_levels_log() for _ in range(3)]
+    np.random.seed(23)
+    ratio = [ru.adjust_random_brightness(img[b], (0.1, 0.3))[1] for b in range(3)]
+    np.random.seed(24)
+    out = np.stack([ru.add_read_and_shot_noise(img[b].astype(np.float64) * ratio[b], levels[b][0], levels[b][1])
+                    for b in range(3)])
+    np.random.seed(24)
+    z = np.random.normal(0, 1, img.shape)                  # the normals np.random.normal(0, scale) scaled
+    np.random.seed(25)
+    lin = ru.random_noise_levels_linear()
+    return dict(img=img, shot=np.array([l[0] for l in levels]), read=np.array([l[1] for l in levels]),
+                gain=np.array(ratio), z=z, out=out, linear=np.array(lin))
+
+
 def main():
     ref = ref_shim.load()
     a = agent_golden(ref)
@@ -240,6 +270,7 @@ def main():
     d = denoise_modules_golden(ref)
     np.savez_compressed(os.path.join(HERE, "denoise_modules.npz"), **d)
     np.savez_compressed(os.path.join(HERE, "denoise_param.npz"), **denoise_param_golden(ref))
+    np.savez_compressed(os.path.join(HERE, "noise_model.npz"), **noise_model_golden())
     for fn in ("filters.npz", "select.npz"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")
 

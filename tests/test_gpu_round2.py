@@ -853,3 +853,53 @@ def test_bare_nlm_modules_api(dev):
     lum = D.rgb_to_luminance(x)
     assert lum.shape == (2, 1, 48, 64)
     assert D.BoxFilter(5, "sum")(lum).shape == lum.shape and D.ShiftStack(3)(lum).shape == (2, 1, 48, 64, 9)
+
+
+# ----------------------------------------------------------------------------------------------
+# 11. shot / read noise of the synthetic-RAW model (isp/unprocess_np.py:131-181) on the resident batch
+# ----------------------------------------------------------------------------------------------
+def test_shot_read_noise_matches_reference_vectors(dev):
+    """aisp_shot_read_noise with the reference's own normals: brightness ratio, then x + sqrt(x*shot + read)*z
+    against the unmodified NumPy module's output (float64 there, fp32 here: 1e-6)."""
+    import os
+    from adaptiveisp_b200 import unprocess as U
+    G = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "noise_model.npz")))
+    img = torch.from_numpy(G["img"]).to(dev)
+    z = torch.from_numpy(G["z"].astype(np.float32)).to(dev)
+    y = U.add_read_and_shot_noise(img, G["shot"], G["read"], gain=G["gain"], z=z)
+    assert np.abs(y.cpu().numpy().astype(np.float64) - G["out"]).max() <= 1e-6
+    # ragged / unaligned sizes take the scalar path; in place is allowed
+    x = torch.rand((2, 3, 7, 9), device=dev)
+    zz = torch.randn_like(x)
+    ref = O.shot_read_noise(x.cpu().numpy(), [0.003, 0.01], [1e-4, 2e-5], zz.cpu().numpy())
+    y2 = U.add_read_and_shot_noise(x.clone(), [0.003, 0.01], [1e-4, 2e-5], z=zz)
+    assert np.abs(y2.cpu().numpy() - ref).max() <= 1e-6
+    xi = x.clone()
+    U.add_read_and_shot_noise(xi, [0.003, 0.01], [1e-4, 2e-5], z=zz, out=xi)
+    assert torch.equal(xi, y2)
+    # a negative variance is NaN, as numpy's sqrt gives
+    neg = torch.full((1, 3, 4, 4), -1.0, device=dev)
+    assert torch.isnan(U.add_read_and_shot_noise(neg, 0.5, 0.1, z=torch.ones_like(neg))).all()
+
+
+def test_shot_read_noise_in_kernel_normals(dev):
+    """Philox normals generated in the kernel: deterministic in (seed, offset), standard-normal moments, and the
+    heteroscedastic variance x * shot + read of isp/unprocess_np.py:178-181 per image."""
+    from adaptiveisp_b200 import unprocess as U
+    B, n = 3, 1 << 20
+    level = torch.tensor([0.05, 0.3, 0.8], device=dev).reshape(B, 1).expand(B, n).contiguous()
+    shot, read = [0.01, 0.002, 0.012], [1e-4, 5e-6, 3e-4]
+    a = U.add_read_and_shot_noise(level, shot, read, seed=7)
+    b = U.add_read_and_shot_noise(level, shot, read, seed=7)
+    c = U.add_read_and_shot_noise(level, shot, read, seed=7, offset=n // 4)
+    d = U.add_read_and_shot_noise(level, shot, read, seed=8)
+    assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, d)
+    for i in range(B):
+        var = float(level[i, 0]) * shot[i] + read[i]
+        zhat = ((a[i] - level[i]) / var ** 0.5).double()
+        assert abs(float(zhat.mean())) <= 5e-3                       # 5 sigma of the mean of 2^20 normals
+        assert abs(float(zhat.var()) - 1.0) <= 1e-2
+        assert abs(float((zhat ** 4).mean()) - 3.0) <= 5e-2          # kurtosis of a normal
+        assert abs(float((zhat[:-1] * zhat[1:]).mean())) <= 5e-3     # neighbours uncorrelated
+    # images get different streams
+    assert abs(float(((a[0] - level[0]) * (a[1] - level[1])).mean())) <= 1e-5

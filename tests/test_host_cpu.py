@@ -32,7 +32,7 @@ def header_symbols():
 def test_library_exports_every_declared_symbol(lib):
     from adaptiveisp_b200 import _lib
     syms = header_symbols()
-    assert len(syms) == 25
+    assert len(syms) == 27
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/aisp_b200.h but not exported"
     assert set(syms) == set(_lib.SIGNATURES), "ctypes binding and header disagree"
