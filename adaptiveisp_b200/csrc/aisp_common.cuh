@@ -143,6 +143,55 @@ __device__ __forceinline__ float min_nan(float a, float b) {
     asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
     return r;
 }
+// ---------------------------------------------------------------------------------------------
+// Blackwell packed fp32 (PTX ISA 8.6, sm_100+; SASS FADD2 / FMUL2 / FFMA2): one instruction, one issue
+// slot, two IEEE round-to-nearest fp32 results (lane-wise identical to the scalar instruction).  A pair
+// lives in an aligned 64-bit register pair: 64 / 128-bit loads deliver pairs for free, scalar producers
+// are packed for free when the register allocator places their destinations side by side.
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 splat2(float v) { return pack2(v, v); }
+__device__ __forceinline__ float lo2(f32x2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    (void)hi;
+    return lo;
+}
+__device__ __forceinline__ float hi2(f32x2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    (void)lo;
+    return hi;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 lds2(const float* p) {   // 8-byte aligned pair from shared memory
+    return *reinterpret_cast<const f32x2*>(p);
+}
+
 // clamp backward: gradient passes iff lo <= y <= hi, inclusive (NaN -> 0)
 __device__ __forceinline__ float pass01(float y) { return (__saturatef(y) == y) ? 1.f : 0.f; }   // see mask01
 

@@ -52,36 +52,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-// Blackwell packed fp32 (PTX ISA 8.6, sm_100+): one instruction, two IEEE fp32 results.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ float lo2(f32x2 v) {
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-    (void)hi;
-    return lo;
-}
-__device__ __forceinline__ float hi2(f32x2 v) {
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-    (void)lo;
-    return hi;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-
 // variant: 0 = DenoiseFilter.process (isp/filters.py:582-586: input clipped, gray distance);
 //   1 = the bare NonLocalMeansGray module (isp/denoise.py:93-119): distances on the luma of the CLIPPED
 //       image (rgb_to_luminance clips, :14), averages of the UNclipped one;
@@ -352,20 +322,6 @@ constexpr int kN2RS = 76;                                // row stride in floats
 constexpr int kN2Plane = kN2SH * kN2RS;
 constexpr int kN2Copy = 4 * kN2Plane;                    // planes: luma, R, G, B
 constexpr int kN2SmemBytes = 2 * kN2Copy * (int)sizeof(float);
-
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ f32x2 lds2(const float* p) {   // 8-byte aligned pair from shared memory
-    return *reinterpret_cast<const f32x2*>(p);
-}
 
 template <bool WITH_GRAD, bool SEQ>
 __global__ void __launch_bounds__(kThreads, 3)

@@ -188,17 +188,201 @@ __device__ __forceinline__ float sharpen_value(int op, float x, float blur, floa
     return x + (x - blur) * f;  // SHARPEN_V2 and USM
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed-pair stencil bodies (round 2).  A thread's four output columns are the ALIGNED pairs
+// (c0, c1), (c2, c3) of its staged row, so every per-pixel quantity is a natural f32x2 and the blur,
+// its sigma-derivative, the sharpen value and the gradient products run as FADD2 / FMUL2 / FFMA2 -- one
+// issue slot per two pixels.  Taps at even offsets of a pair are pairs again; the +-1 taps are the
+// mixed sums (c-1 + c1, c0 + c2), formed by two scalar adds whose results the register allocator
+// places side by side.  USM runs the vertical 5-tap pass first (pure pair arithmetic on the loaded
+// columns), then the horizontal one on two rows.
+//   pl: plane base + by * kCpW + bx + kColOff (column c0 of the thread's first staged row, 16-byte aligned)
+// ---------------------------------------------------------------------------------------------
+template <bool WITH_D>
+__device__ __forceinline__ void usm_block2(const float* pl, const float* sc, f32x2 (&xc)[2][2], f32x2 (&blur)[2][2],
+                                           f32x2 (&dblur)[2][2]) {
+    const f32x2 k0 = splat2(sc[0]), k1 = splat2(sc[1]), k2 = splat2(sc[2]);
+    const f32x2 d0 = splat2(sc[5]), d1 = splat2(sc[6]), d2 = splat2(sc[7]);
+    f32x2 VK[2][4], VD[2][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {   // column pairs (c-2, c-1), (c0, c1), (c2, c3), (c4, c5)
+        f32x2 V[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) V[r] = lds2(pl + r * kCpW - 2 + 2 * p);
+        if (p == 1 || p == 2) { xc[0][p - 1] = V[2]; xc[1][p - 1] = V[3]; }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const f32x2 e2 = add2(V[r], V[r + 4]), e1 = add2(V[r + 1], V[r + 3]), e0 = V[r + 2];
+            VK[r][p] = fma2(k0, e2, fma2(k1, e1, mul2(k2, e0)));
+            if (WITH_D) VD[r][p] = fma2(d0, e2, fma2(d1, e1, mul2(d2, e0)));
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const f32x2 L = VK[r][q], C = VK[r][q + 1], R = VK[r][q + 2];
+            const f32x2 e2 = add2(L, R);
+            const f32x2 e1 = pack2(hi2(L) + hi2(C), lo2(C) + lo2(R));
+            blur[r][q] = fma2(k0, e2, fma2(k1, e1, mul2(k2, C)));
+            if (WITH_D) {   // d(kv (x) kh) = dkv (x) kh + kv (x) dkh
+                const f32x2 hd = fma2(d0, e2, fma2(d1, e1, mul2(d2, C)));
+                const f32x2 LD = VD[r][q], CD = VD[r][q + 1], RD = VD[r][q + 2];
+                const f32x2 f2 = add2(LD, RD);
+                const f32x2 f1 = pack2(hi2(LD) + hi2(CD), lo2(CD) + lo2(RD));
+                dblur[r][q] = add2(hd, fma2(k0, f2, fma2(k1, f1, mul2(k2, CD))));
+            }
+        }
+}
+
+// frame pixels of a thread's 4x2 block as a bit mask (bit 4r + i: output (r, i) lies on the image frame)
+__device__ __forceinline__ unsigned frame_bits(int gx0, int gy0, int H, int W) {
+    unsigned m = 0;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int gy = gy0 + r, gx = gx0 + i;
+            if ((gy == 0) || (gy == H - 1) || (gx == 0) || (gx == W - 1)) m |= 1u << (4 * r + i);
+        }
+    return m;
+}
+
+// 3x3: vertical 3-row sums of the column pairs first (rows 1, 2 of the window are shared by both output
+// rows), then the horizontal sum; ring = box9 - x, blur = ring / 13 + 5 x / 13 (isp/sharpen.py:105-142)
+template <bool FRAME>
+__device__ __forceinline__ void box3_block2(const float* pl, unsigned fbits, f32x2 (&xc)[2][2], f32x2 (&blur)[2][2]) {
+    const f32x2 a = splat2(1.0f / 13.0f), bc = splat2(5.0f / 13.0f);
+    f32x2 VS[2][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {   // column pairs (c-2, c-1), (c0, c1), (c2, c3), (c4, c5)
+        f32x2 V[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) V[r] = lds2(pl + (1 + r) * kCpW - 2 + 2 * p);
+        if (p == 1 || p == 2) { xc[0][p - 1] = V[1]; xc[1][p - 1] = V[2]; }
+        const f32x2 m = add2(V[1], V[2]);
+        VS[0][p] = add2(V[0], m);
+        VS[1][p] = add2(m, V[3]);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const f32x2 L = VS[r][q], C = VS[r][q + 1], R = VS[r][q + 2];
+            const f32x2 x = xc[r][q];
+            const f32x2 box = add2(pack2(hi2(L) + hi2(C), lo2(C) + lo2(R)), C);
+            f32x2 bl = fma2(a, sub2(box, x), mul2(bc, x));
+            if (FRAME) {  // only threads that own a frame pixel pay for the pass-through select
+                const unsigned two = (fbits >> (4 * r + 2 * q)) & 3u;
+                if (two) bl = pack2((two & 1u) ? lo2(x) : lo2(bl), (two & 2u) ? hi2(x) : hi2(bl));
+            }
+            blur[r][q] = bl;
+        }
+}
+
+// One thread's 4x2 block of all three planes.  FULL: the tile lies inside the image, rows are 16-byte
+// multiples, the upstream gradient sits in shared memory and no pooled gradient is folded in.
+// KIND: 0 = 3x3 away from the frame, 1 = 3x3 on a frame tile, 2 = 5x5 USM.
+template <bool BWD, bool WRITE_GY, bool FULL, int KIND>
+__device__ __forceinline__ void sharpen_tile(const float* tile, const float* gtile, const float* sc, int op, int H, int W,
+                                             int gx0, int gy0, int b, size_t base, bool vec_ok, bool g_tma,
+                                             const float* __restrict__ gout, float* __restrict__ out,
+                                             const PooledGrad& pool, float (&acc)[2]) {
+    constexpr bool usm = (KIND == 2);
+    const float fs = usm ? sc[10] : sc[0];
+    const f32x2 f = splat2(fs), omf = splat2(1.0f - fs), zero2 = splat2(0.f);
+    const bool blend = (op == AISP_OP_SHARPEN);          // x*f + blur*(1-f); otherwise x + (x - blur)*f
+    const unsigned fbits = (KIND == 1) ? frame_bits(gx0, gy0, H, W) : 0u;
+    f32x2 acc0 = zero2, acc1 = zero2;
+#pragma unroll 1
+    for (int ch = 0; ch < 3; ++ch) {
+        f32x2 xc[2][2], blur[2][2], dblur[2][2];
+        const float* pl = tile + ch * kSmH * kCpW;
+        if (usm) usm_block2<BWD>(pl, sc, xc, blur, dblur);
+        else box3_block2<KIND == 1>(pl, fbits, xc, blur);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int gy = gy0 + r;
+            const size_t off = base + ((size_t)ch * H + gy) * W + gx0;
+            const bool row_ok = FULL || ((gy < H) && (gx0 < W));
+            f32x2 y[2], xmb[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const f32x2 x = xc[r][q];
+                xmb[q] = sub2(x, blur[r][q]);
+                // products rounded, then added, as the reference's ATen expressions are
+                const f32x2 v = (!usm && blend) ? add2(mul2(x, f), mul2(blur[r][q], omf)) : add2(x, mul2(xmb[q], f));
+                y[q] = fma2(zero2, x, v);   // 0 * x: the (1 - mask) * img term of the reference's lerp (NaN iff x is inf / NaN)
+            }
+            if (!BWD) {
+                if (!row_ok) continue;
+                const float o0 = clip01(lo2(y[0])), o1 = clip01(hi2(y[0])), o2 = clip01(lo2(y[1])), o3 = clip01(hi2(y[1]));
+                if (FULL || vec_ok) {
+                    stg_stream4(out + off, make_float4(o0, o1, o2, o3));
+                } else {
+                    const float o[4] = {o0, o1, o2, o3};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (gx0 + i < W) out[off + i] = o[i];
+                }
+            } else {
+                float g[4];
+                if (FULL || g_tma) {   // staged by TMA: zero beyond the image
+                    const float4 t = *reinterpret_cast<const float4*>(gtile + (ch * kShTileH + r) * kShTileW);
+                    g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) g[i] = (row_ok && gx0 + i < W) ? gout[off + i] : 0.f;
+                }
+                if (!FULL && pool.g && row_ok) {   // + the gradient of the pooled image
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (gx0 + i < W) g[i] += pooled_at(pool, b, ch, gy, gx0 + i);
+                }
+                g[0] *= pass01(lo2(y[0])); g[1] *= pass01(hi2(y[0]));
+                g[2] *= pass01(lo2(y[1])); g[3] *= pass01(hi2(y[1]));
+                const f32x2 ga = pack2(g[0], g[1]), gb = pack2(g[2], g[3]);
+                if (usm) {
+                    acc0 = fma2(ga, dblur[r][0], acc0); acc0 = fma2(gb, dblur[r][1], acc0);
+                    acc1 = fma2(ga, xmb[0], acc1); acc1 = fma2(gb, xmb[1], acc1);
+                } else {
+                    acc0 = fma2(ga, xmb[0], acc0); acc0 = fma2(gb, xmb[1], acc0);
+                }
+                if (WRITE_GY && row_ok) {
+                    if (FULL || vec_ok) {
+                        stg_stream4(out + off, make_float4(g[0], g[1], g[2], g[3]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (gx0 + i < W) out[off + i] = g[i];
+                    }
+                }
+            }
+        }
+    }
+    acc[0] = lo2(acc0) + hi2(acc0);
+    acc[1] = lo2(acc1) + hi2(acc1);
+}
+
+// dynamic shared memory of sharpen_kernel: image tile + halo | upstream-gradient tile (backward) | constants | reduction rows
+constexpr int kGoFloats = 3 * kShTileH * kShTileW;                        // 24 KB
+constexpr unsigned kGoBytes = kGoFloats * sizeof(float);
+constexpr size_t kShSmemFwd = (size_t)(kSmFloats + kConst) * sizeof(float) + 16;
+constexpr size_t kShSmemBwd = (size_t)(kSmFloats + kGoFloats + kConst + kWarps * AISP_ACC_STRIDE) * sizeof(float) + 16;
+
 template <bool BWD, bool WRITE_GY>
 __global__ void __launch_bounds__(kThreads, BWD ? 3 : 4)
-sharpen_kernel(const __grid_constant__ CUtensorMap tmap, int tma_ok, const float* __restrict__ img,
-               const float* __restrict__ gout, float* __restrict__ out, const float* __restrict__ params,
-               const int32_t* __restrict__ ops, int H, int W, int vec, float* __restrict__ partial, BankMap bm,
-               PooledGrad pool) {
+sharpen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap gmap, int tma_ok,
+               const float* __restrict__ img, const float* __restrict__ gout, float* __restrict__ out,
+               const float* __restrict__ params, const int32_t* __restrict__ ops, int H, int W, int vec,
+               float* __restrict__ partial, BankMap bm, PooledGrad pool) {
     pdl_prologue();
-    __shared__ __align__(128) float sm[kSmFloats];
-    __shared__ __align__(8) unsigned long long bar;
-    __shared__ float sc[kConst];
-    __shared__ float red[kWarps * AISP_ACC_STRIDE];
+    extern __shared__ __align__(128) float shsm[];
+    float* sm = shsm;                                            // [3][kSmH][kCpW]
+    float* gs = shsm + kSmFloats;                                // [3][kShTileH][kShTileW]  (backward, TMA path)
+    float* sc = shsm + kSmFloats + (BWD ? kGoFloats : 0);        // [kConst]
+    float* red = sc + kConst;                                    // [kWarps][AISP_ACC_STRIDE]  (backward)
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(red + (BWD ? kWarps * AISP_ACC_STRIDE : 0));
     const int b = bank_sample(bm, blockIdx.z);   // filter-bank launches: see BankMap
     const int op = sample_op(ops, bm, b);
     if (!is_sharpen(op)) return;
@@ -210,14 +394,18 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, int tma_ok, const float
     // y0 + 17 == H outside although the tile itself ends one row short of the frame)
     const bool usm_halo_out = (x0 < kHalo) || (y0 < kHalo) || (x0 + kShTileW + kHalo > W) || (y0 + kShTileH + kHalo > H);
     const bool use_tma = tma_ok && !(op == AISP_OP_USM && usm_halo_out);
-    if (use_tma) {
-        if (threadIdx.x == 0) mbar_init(&bar, 1);
+    // the upstream gradient rides on TMA whenever the launch can (its zero fill makes rows / columns past the
+    // image contribute nothing); tma_ok covers both maps
+    const bool g_tma = BWD && tma_ok;
+    if (tma_ok) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
         __syncthreads();
         if (threadIdx.x == 0) {
-            mbar_expect_tx(&bar, kTmaBytes);
-            tma_load_3d(sm, &tmap, x0 - kColOff, y0 - kHalo, (b / bm.F) * 3, &bar);
+            mbar_expect_tx(bar, (use_tma ? kTmaBytes : 0u) + (g_tma ? kGoBytes : 0u));
+            if (use_tma) tma_load_3d(sm, &tmap, x0 - kColOff, y0 - kHalo, (b / bm.F) * 3, bar);
+            if (g_tma) tma_load_3d(gs, &gmap, x0, y0, b * 3, bar);
         }
-        // one wave ahead: the tile that a CTA scheduled ~one machine-fill later will load goes to L2 now
+        // one wave ahead: the tiles that a CTA scheduled ~one machine-fill later will load go to L2 now
         if (threadIdx.x == 32) {
             const int ahead = 148 * (BWD ? 3 : 4);
             int lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + ahead;
@@ -226,111 +414,46 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, int tma_ok, const float
             const int py = lin % gridDim.y, pz = lin / gridDim.y;
             if (pz < (int)gridDim.z) {
                 const int pb = bank_sample(bm, pz);
-                if (is_sharpen(sample_op(ops, bm, pb)))
+                if (is_sharpen(sample_op(ops, bm, pb))) {
                     tma_prefetch_3d(&tmap, px * kShTileW - kColOff, py * kShTileH - kHalo, (pb / bm.F) * 3);
+                    if (BWD) tma_prefetch_3d(&gmap, px * kShTileW, py * kShTileH, pb * 3);
+                }
             }
         }
-    } else {
-        stage_tile_cp(img + (size_t)(b / bm.F) * 3 * H * W, sm, H, W, x0, y0, vec != 0);
     }
+    if (!use_tma) stage_tile_cp(img + (size_t)(b / bm.F) * 3 * H * W, sm, H, W, x0, y0, vec != 0);
     load_consts(params, b, op, sc);
 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int bx = tx * 4, by = ty * 2;
     const int gx0 = x0 + bx, gy0 = y0 + by;
     const bool vec_ok = vec && (gx0 + 3 < W);  // vec: W % 4 == 0 and 16B-aligned global pointers
-    float acc[2] = {0.f, 0.f};
-    // upstream gradient of this thread's 3 x 2 x 4 outputs: requested before the tile has landed
-    float gpre[3][2][4];
-    if (BWD) {
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch)
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int gy = gy0 + r;
-                const size_t off = base + ((size_t)ch * H + gy) * W + gx0;
-                if (gy < H && vec_ok) {
-                    const float4 t = ldg_stream4(gout + off);
-                    gpre[ch][r][0] = t.x; gpre[ch][r][1] = t.y; gpre[ch][r][2] = t.z; gpre[ch][r][3] = t.w;
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        gpre[ch][r][i] = (gy < H && gx0 + i < W) ? gout[off + i] : 0.f;
-                }
-                if (pool.g && gy < H) {   // + the gradient of the pooled image
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (gx0 + i < W) gpre[ch][r][i] += pooled_at(pool, b, ch, gy, gx0 + i);
-                }
-            }
-    }
-    if (use_tma) {
-        mbar_wait(&bar, 0);
-    } else {
-        cp_async_wait_all();
-    }
+    if (!use_tma) cp_async_wait_all();
+    if (tma_ok) mbar_wait(bar, 0);
     __syncthreads();
-    const float f = (op == AISP_OP_USM) ? sc[10] : sc[0];
-
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        float xc[2][4], blur[2][4], dblur[2][4];
-        const float* pl = sm + ch * kSmH * kCpW;
-        if (op == AISP_OP_USM)
-            block_blur<true, BWD, false, kCpW, kColOff>(pl, bx, by, sc, gx0, gy0, H, W, xc, blur, dblur);
-        else if (frame_tile)
-            block_blur<false, BWD, true, kCpW, kColOff>(pl, bx, by, sc, gx0, gy0, H, W, xc, blur, dblur);
-        else
-            block_blur<false, BWD, false, kCpW, kColOff>(pl, bx, by, sc, gx0, gy0, H, W, xc, blur, dblur);
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int gy = gy0 + r;
-            if (gy >= H || gx0 >= W) continue;
-            const size_t off = base + ((size_t)ch * H + gy) * W + gx0;
-            float y[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)   // 0 * x: the (1 - mask) * img term of the reference's lerp (NaN iff x is inf / NaN)
-                y[i] = fmaf(0.f, xc[r][i], sharpen_value(op, xc[r][i], blur[r][i], f));
-            if (!BWD) {
-                if (vec_ok) {
-                    stg_stream4(out + off, make_float4(clip01(y[0]), clip01(y[1]), clip01(y[2]), clip01(y[3])));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (gx0 + i < W) out[off + i] = clip01(y[i]);
-                }
-            } else {
-                float g[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) g[i] = gpre[ch][r][i];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    g[i] *= pass01(y[i]);
-                    if (gx0 + i < W) {
-                        if (op == AISP_OP_USM) {
-                            acc[0] = fmaf(g[i], dblur[r][i], acc[0]);
-                            acc[1] = fmaf(g[i], xc[r][i] - blur[r][i], acc[1]);
-                        } else {
-                            acc[0] = fmaf(g[i], xc[r][i] - blur[r][i], acc[0]);
-                        }
-                    }
-                }
-                if (WRITE_GY) {
-                    if (vec_ok) {
-                        stg_stream4(out + off, make_float4(g[0], g[1], g[2], g[3]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (gx0 + i < W) out[off + i] = g[i];
-                    }
-                }
-            }
-        }
+    float acc[2] = {0.f, 0.f};
+    // CTA-uniform specialisation: whole tile inside the image with 128-bit accesses (no per-row / per-column
+    // tests), and the stencil kind (5x5 USM, 3x3 away from the frame, 3x3 on the frame)
+    const bool full = vec && (x0 + kShTileW <= W) && (y0 + kShTileH <= H) && (!BWD || g_tma) && !pool.g;
+    const int kind = (op == AISP_OP_USM) ? 2 : (frame_tile ? 1 : 0);
+    const float* tile = sm + by * kCpW + bx + kColOff;
+    const float* gtile = gs + by * kShTileW + bx;
+#define AISP_SHARPEN_TILE(FULL, KIND)                                                                                    \
+    sharpen_tile<BWD, WRITE_GY, FULL, KIND>(tile, gtile, sc, op, H, W, gx0, gy0, b, base, vec_ok, g_tma, gout, out, pool, acc)
+    if (full) {
+        if (kind == 2) AISP_SHARPEN_TILE(true, 2);
+        else if (kind == 1) AISP_SHARPEN_TILE(true, 1);
+        else AISP_SHARPEN_TILE(true, 0);
+    } else {
+        if (kind == 2) AISP_SHARPEN_TILE(false, 2);
+        else if (kind == 1) AISP_SHARPEN_TILE(false, 1);
+        else AISP_SHARPEN_TILE(false, 0);
     }
+#undef AISP_SHARPEN_TILE
     if (BWD) {
-        const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+        const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
         const int ntiles = gridDim.x * gridDim.y;
-        block_reduce_store<2>(acc, red, partial + ((size_t)b * ntiles + tile) * AISP_ACC_STRIDE);
+        block_reduce_store<2>(acc, red, partial + ((size_t)b * ntiles + tile_id) * AISP_ACC_STRIDE);
     }
 }
 
@@ -490,128 +613,166 @@ sharpen_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------
-// transposed stencil: grad_img from the masked upstream gradient gy (staged by the kernel above)
-// CTA <-> (sample, 128x8 tile); a thread owns a 1x4 strip of all three planes and evaluates the transposed
-// stencil separably from registers (5 rows x 8 staged values per plane): the 5x5 Gaussian is k (x) k, the
-// 3x3 kernel is (ones3x3 + 4 delta) / 13.  Reflect-padding mirrors (USM, pixels within 2 of the frame) are
-// folded in per pixel from global memory -- a few pixels per row.
+// transposed stencil: grad_img from the masked upstream gradient gy (written by sharpen_kernel<true, true>)
+// Same geometry as the forward: CTA <-> (sample, 128x16 tile); tile + 2-px halo of the three gy planes is
+// staged by ONE TMA copy -- its zero fill outside the image is exactly the zero extension a transposed
+// correlation needs -- and a thread produces a 4x2 block per plane from registers, 128-bit stores.
+//   * 5x5 USM is k (x) k.  Reflect padding is separable too (rows are padded, then columns), so its adjoint
+//     folds per axis: output index q collects the padded positions q' that reflect onto it,
+//         w_q(rho) = k(q - rho) + sum_{q' in mirrors(q)} k(q' - rho),   mirrors: 1 -> -1, 2 -> -2, n-2 -> n, n-3 -> n+1,
+//     i.e. outputs 1, 2, n-3, n-2 of an axis get one or two extra taps (k1 gy(0) + k0 gy(1); k0 gy(0);
+//     k0 gy(n-1); k0 gy(n-2) + k1 gy(n-1)) on top of the plain separable pass -- a few predicated FMAs in the
+//     threads next to the frame; tiles away from the frame never test for them.
+//   * the 3x3 kernel is (ones3x3 + 4 delta) / 13; frame pixels pass x through (isp/sharpen.py:105-142), so
+//     their gy does not flow through the blur (masked as it is read) and reaches grad_img directly.
 // ---------------------------------------------------------------------------------------------
-constexpr int kAdjW = 128, kAdjH = 8, kAdjSW = kAdjW + 8;   // staged row: tile column 0 at smem column 4
-
-__device__ __forceinline__ float gy_valid(const float* __restrict__ gy, int op, int H, int W, int y, int x) {
-    // gradient of output pixel (y,x) that flows through its blur term
-    if (y < 0 || y >= H || x < 0 || x >= W) return 0.f;
-    if (op != AISP_OP_USM && (y == 0 || x == 0 || y == H - 1 || x == W - 1)) return 0.f;  // border: blur == x
-    return gy[(size_t)y * W + x];
-}
-
-__device__ inline float gpad_at(const float* __restrict__ gy, int op, const float (*w)[5], int H, int W, int y,
-                                int x) {
-    // sum_k K(k) * gy(y - k): transposed correlation evaluated at a (possibly padded) position
-    float s = 0.f;
-    for (int dy = -2; dy <= 2; ++dy)
-        for (int dx = -2; dx <= 2; ++dx) s = fmaf(w[dy + 2][dx + 2], gy_valid(gy, op, H, W, y - dy, x - dx), s);
-    return s;
-}
-
-__device__ __forceinline__ int mirrors(int q, int n, int* m) {
-    // padded indices q' in [-2, n+1] whose reflect source is q (besides q itself)
-    int c = 0;
-    if (q >= 1 && q <= 2) m[c++] = -q;
-    const int hi = 2 * (n - 1) - q;
-    if (hi >= n && hi <= n + 1) m[c++] = hi;
-    return c;
-}
-
-__global__ void __launch_bounds__(kThreads)
-sharpen_adjoint_kernel(const float* __restrict__ gy, float* __restrict__ gimg, const float* __restrict__ params,
-                       const int32_t* __restrict__ ops, int H, int W) {
-    pdl_prologue();
-    __shared__ float sm[3][kAdjH + 4][kAdjSW];
-    __shared__ float sc[kConst];
-    __shared__ float wk[5][5];
-    const int b = blockIdx.z;
-    const int op = ops[b];
-    if (!is_sharpen(op)) return;
-    const int x0 = blockIdx.x * kAdjW, y0 = blockIdx.y * kAdjH;
-    const size_t base = (size_t)b * 3 * H * W;
-    load_consts(params, b, op, sc);
-    __syncthreads();
-    if (threadIdx.x < 25) {   // dense 5x5 weights: only the mirror terms of frame pixels use them
-        const int i = threadIdx.x / 5, j = threadIdx.x % 5;
-        float v;
-        if (op == AISP_OP_USM) v = sc[i] * sc[j];
-        else v = (i == 0 || i == 4 || j == 0 || j == 4) ? 0.f : ((i == 2 && j == 2) ? 5.0f / 13.0f : 1.0f / 13.0f);
-        wk[i][j] = v;
+// staging without TMA (rows that are not 16-byte multiples): zero fill outside the image
+__device__ __forceinline__ void stage_tile_zero(const float* __restrict__ src, float* sm, int H, int W, int x0, int y0) {
+    constexpr int kPlane = kSmH * kCpW;
+    for (int e = threadIdx.x; e < 3 * kPlane; e += kThreads) {
+        const int ch = e / kPlane, rem = e - ch * kPlane;
+        const int row = rem / kCpW, col = rem - row * kCpW;
+        const int y = y0 - kHalo + row, x = x0 - kColOff + col;
+        sm[e] = (y >= 0 && y < H && x >= 0 && x < W) ? src[((size_t)ch * H + y) * W + x] : 0.f;
     }
-    constexpr int kCols = kAdjW + 4;   // staged columns x0-2 .. x0+kAdjW+1 live at smem columns 2 .. kAdjW+5
-    for (int e = threadIdx.x; e < 3 * (kAdjH + 4) * kCols; e += kThreads) {
-        const int ch = e / ((kAdjH + 4) * kCols);
-        const int rem = e - ch * ((kAdjH + 4) * kCols);
-        const int row = rem / kCols, col = rem - row * kCols;
-        sm[ch][row][col + 2] = gy_valid(gy + base + (size_t)ch * H * W, op, H, W, y0 - 2 + row, x0 - 2 + col);
-    }
-    __syncthreads();
-    const int lx = (threadIdx.x & 31) * 4, ly = threadIdx.x >> 5;
-    const int xs = x0 + lx, y = y0 + ly;
-    if (xs >= W || y >= H) return;
+}
+
+// extra taps of the reflect fold for output index q of an axis of length n; t[j] is the value at q - 2 + j
+__device__ __forceinline__ float fold_extra(int q, int n, float k0, float k1, float t0, float t1, float t2, float t3,
+                                            float t4) {
+    float e = 0.f;
+    if (q == 1) e = fmaf(k1, t1, fmaf(k0, t2, e));          // q' = -1 reads gy(0), gy(1)
+    if (q == 2) e = fmaf(k0, t0, e);                        // q' = -2 reads gy(0)
+    if (q == n - 2) e = fmaf(k0, t2, fmaf(k1, t3, e));      // q' = n reads gy(n-2), gy(n-1)
+    if (q == n - 3) e = fmaf(k0, t4, e);                    // q' = n+1 reads gy(n-1)
+    return e;
+}
+
+template <bool FRAME>
+__device__ __forceinline__ void adjoint_block(const float* sm, const float* sc, int op, int H, int W, int gx0, int gy0,
+                                              int bx, int by, float* __restrict__ dst /* sample base of grad_img */,
+                                              bool vec_ok) {
+    const bool usm = (op == AISP_OP_USM);
     float alpha, beta;
     if (op == AISP_OP_SHARPEN) { alpha = sc[0]; beta = 1.0f - sc[0]; }
     else if (op == AISP_OP_SHARPEN_V2) { alpha = 1.0f + sc[0]; beta = -sc[0]; }
     else { alpha = 1.0f + sc[10]; beta = -sc[10]; }
-    const bool usm = (op == AISP_OP_USM);
     const float k0 = sc[0], k1 = sc[1], k2 = sc[2];
-    int my[2];
-    const int nmy = usm ? mirrors(y, H, my) : 0;
+    // per-thread: does the 4x2 block hold an output that collects mirror taps (USM) ...
+    const bool near_x = FRAME && usm && ((gx0 <= 2) || (gx0 + 3 >= W - 3));
+    const bool near_y = FRAME && usm && ((gy0 <= 2) || (gy0 + 1 >= H - 3));
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-        const float* gch = gy + base + (size_t)ch * H * W;
-        // rows y-2 .. y+2, columns xs-2 .. xs+5 of the masked gradient
-        float v[5][8];
+        const float* pl = sm + ch * kSmH * kCpW + by * kCpW + bx + kColOff - 2;   // 8-byte aligned
+        float hrow[6][4], g0[2][4], ctr[2][4];
 #pragma unroll
-        for (int r = 0; r < 5; ++r)
+        for (int r = 0; r < 6; ++r) {
+            float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[r][i] = sm[ch][ly + r][lx + 2 + i];
-        float s[4];
-        if (usm) {
-            float hrow[5][4];
+            for (int i = 0; i < 8; i += 2) {
+                const float2 t = *reinterpret_cast<const float2*>(pl + r * kCpW + i);
+                v[i] = t.x; v[i + 1] = t.y;
+            }
+            if (r >= 2 && r < 4) {
 #pragma unroll
-            for (int r = 0; r < 5; ++r)
+                for (int i = 0; i < 4; ++i) g0[r - 2][i] = v[i + 2];
+            }
+            if (usm) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    hrow[r][i] = fmaf(k0, v[r][i] + v[r][i + 4], fmaf(k1, v[r][i + 1] + v[r][i + 3], k2 * v[r][i + 2]));
+                    hrow[r][i] = fmaf(k0, v[i] + v[i + 4], fmaf(k1, v[i + 1] + v[i + 3], k2 * v[i + 2]));
+                if (near_x) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                s[i] = fmaf(k0, hrow[0][i] + hrow[4][i], fmaf(k1, hrow[1][i] + hrow[3][i], k2 * hrow[2][i]));
-        } else {
+                    for (int i = 0; i < 4; ++i)
+                        hrow[r][i] += fold_extra(gx0 + i, W, k0, k1, v[i], v[i + 1], v[i + 2], v[i + 3], v[i + 4]);
+                }
+            } else {
+                if (FRAME) {   // ... or a frame pixel, whose gy does not flow through the blur (3x3)
+                    const int y = gy0 - 2 + r;
+                    const bool rowf = (y == 0) || (y == H - 1);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int x = gx0 - 2 + i;
+                        v[i] = (rowf || (x == 0) || (x == W - 1)) ? 0.f : v[i];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) hrow[r][i] = (v[i + 1] + v[i + 2]) + v[i + 3];
+                if (r >= 2 && r < 4) {   // centre tap: the (masked) value itself
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) ctr[r - 2][i] = v[i + 2];
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int gy = gy0 + r;
+            if (gy >= H) continue;
+            float o[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                float box = 0.f;
-#pragma unroll
-                for (int r = 1; r < 4; ++r) box += (v[r][i + 1] + v[r][i + 2]) + v[r][i + 3];
-                s[i] = fmaf(4.0f / 13.0f, v[2][i + 2], box * (1.0f / 13.0f));
+                float s;
+                if (usm) {
+                    s = fmaf(k0, hrow[r][i] + hrow[r + 4][i], fmaf(k1, hrow[r + 1][i] + hrow[r + 3][i], k2 * hrow[r + 2][i]));
+                    if (near_y) s += fold_extra(gy, H, k0, k1, hrow[r][i], hrow[r + 1][i], hrow[r + 2][i], hrow[r + 3][i], hrow[r + 4][i]);
+                } else {
+                    const float box = (hrow[r + 1][i] + hrow[r + 2][i]) + hrow[r + 3][i];
+                    s = fmaf(4.0f / 13.0f, ctr[r][i], box * (1.0f / 13.0f));
+                }
+                o[i] = alpha * g0[r][i] + beta * s;
+                if (FRAME && !usm) {
+                    const int x = gx0 + i;
+                    if ((x == 0) || (gy == 0) || (x == W - 1) || (gy == H - 1)) o[i] += beta * g0[r][i];
+                }
             }
-        }
+            float* q = dst + ((size_t)ch * H + gy) * W + gx0;
+            if (vec_ok) {
+                stg_stream4(q, make_float4(o[0], o[1], o[2], o[3]));
+            } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int x = xs + i;
-            if (x >= W) continue;
-            float si = s[i];
-            if (usm) {   // reflect padding folds the halo of the padded plane back onto its mirror pixels
-                int mx[2];
-                const int nmx = mirrors(x, W, mx);
-                for (int a = 0; a < nmy; ++a) si += gpad_at(gch, op, wk, H, W, my[a], x);
-                for (int c2 = 0; c2 < nmx; ++c2) si += gpad_at(gch, op, wk, H, W, y, mx[c2]);
-                for (int a = 0; a < nmy; ++a)
-                    for (int c2 = 0; c2 < nmx; ++c2) si += gpad_at(gch, op, wk, H, W, my[a], mx[c2]);
+                for (int i = 0; i < 4; ++i)
+                    if (gx0 + i < W) q[i] = o[i];
             }
-            const float g0 = gch[(size_t)y * W + x];
-            float out = alpha * g0 + beta * si;
-            const bool border = (x == 0) || (y == 0) || (x == W - 1) || (y == H - 1);
-            if (!usm && border) out += beta * g0;
-            gimg[base + ((size_t)ch * H + y) * W + x] = out;
         }
     }
+}
+
+__global__ void __launch_bounds__(kThreads, 3)
+sharpen_adjoint_kernel(const __grid_constant__ CUtensorMap tmap, int tma_ok, const float* __restrict__ gy,
+                       float* __restrict__ gimg, const float* __restrict__ params, const int32_t* __restrict__ ops, int H,
+                       int W, int vec) {
+    pdl_prologue();
+    __shared__ __align__(128) float sm[kSmFloats];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ float sc[kConst];
+    const int b = blockIdx.z;
+    const int op = ops[b];
+    if (!is_sharpen(op)) return;
+    const int x0 = blockIdx.x * kShTileW, y0 = blockIdx.y * kShTileH;
+    const size_t base = (size_t)b * 3 * H * W;
+    if (tma_ok) {
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, kTmaBytes);
+            tma_load_3d(sm, &tmap, x0 - kColOff, y0 - kHalo, b * 3, &bar);
+        }
+    } else {
+        stage_tile_zero(gy + base, sm, H, W, x0, y0);
+    }
+    load_consts(params, b, op, sc);
+    if (tma_ok) mbar_wait(&bar, 0);
+    __syncthreads();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int bx = tx * 4, by = ty * 2;
+    const int gx0 = x0 + bx, gy0 = y0 + by;
+    if (gx0 >= W || gy0 >= H) return;
+    const bool vec_ok = vec && (gx0 + 3 < W);
+    // CTA-uniform: does the tile hold an output within 3 pixels of the image frame?  (USM outputs 1, 2, n-3, n-2 of an
+    // axis collect mirror taps; 3x3 outputs next to the frame read masked frame pixels)
+    const bool frame = (x0 <= kHalo) || (y0 <= kHalo) || (x0 + kShTileW + kHalo >= W) || (y0 + kShTileH + kHalo >= H);
+    if (frame) adjoint_block<true>(sm, sc, op, H, W, gx0, gy0, bx, by, gimg + base, vec_ok);
+    else adjoint_block<false>(sm, sc, op, H, W, gx0, gy0, bx, by, gimg + base, vec_ok);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -649,17 +810,29 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-static bool make_tile_map(CUtensorMap* map, const float* img, int B, int H, int W) {
+static bool make_tile_map(CUtensorMap* map, const float* img, int B, int H, int W, int box_w = kTmaW, int box_h = kSmH) {
     memset(map, 0, sizeof(*map));
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn || (W & 3) != 0 || !al16(img) || W < 4) return false;
     const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * 3};
     const cuuint64_t gstr[2] = {(cuuint64_t)W * sizeof(float), (cuuint64_t)W * H * sizeof(float)};
-    const cuuint32_t box[3] = {(cuuint32_t)kTmaW, (cuuint32_t)kSmH, 3};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 3};
     const cuuint32_t estr[3] = {1, 1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(img), gdim, gstr, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <bool BWD, bool WRITE_GY>
+static void sharpen_attrs() {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !done[dev]) {
+        cudaFuncSetAttribute(sharpen_kernel<BWD, WRITE_GY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(BWD ? kShSmemBwd : kShSmemFwd));
+        done[dev] = true;
+    }
 }
 
 cudaError_t launch_sharpen_fwd(const float* img, float* out, const float* params, const int32_t* ops, int B, int H,
@@ -668,9 +841,9 @@ cudaError_t launch_sharpen_fwd(const float* img, float* out, const float* params
     const int vec = ((W & 3) == 0) && al16(img) && al16(out);
     CUtensorMap map;
     const int tma_ok = make_tile_map(&map, img, bm.n ? B / bm.n : B, H, W) ? 1 : 0;
-    launch_pdl(sharpen_kernel<false, false>, grid, kThreads, st, map, tma_ok, img, nullptr, out, params, ops, H, W, vec,
-               nullptr, bm, no_pooled_grad());
-    return cudaGetLastError();
+    sharpen_attrs<false, false>();
+    return launch_pdl_smem(sharpen_kernel<false, false>, grid, kThreads, kShSmemFwd, st, map, map, tma_ok, img, nullptr, out,
+                           params, ops, H, W, vec, nullptr, bm, no_pooled_grad());
 }
 
 // Sequence forward over one or two jobs (job 1 = the high-resolution twin, hr_img == nullptr: absent).
@@ -716,21 +889,29 @@ cudaError_t launch_sharpen_bwd(const float* img, const float* gout, const float*
                                BankMap bm, PooledGrad pool, cudaStream_t st) {
     dim3 grid((W + kShTileW - 1) / kShTileW, (H + kShTileH - 1) / kShTileH, B);
     const int vec = ((W & 3) == 0) && al16(img) && al16(gout) && (!grad_img || al16(gy_scratch));
-    CUtensorMap map;
-    const int tma_ok = make_tile_map(&map, img, bm.n ? B / bm.n : B, H, W) ? 1 : 0;
-    if (grad_img)
-        launch_pdl(sharpen_kernel<true, true>, grid, kThreads, st, map, tma_ok, img, gout, gy_scratch, params, ops, H, W, vec,
-                   partial, bm, pool);
-    else
-        launch_pdl(sharpen_kernel<true, false>, grid, kThreads, st, map, tma_ok, img, gout, nullptr, params, ops, H, W, vec,
-                   partial, bm, pool);
+    CUtensorMap map, gmap;
+    // the upstream gradient is [virtual samples, 3, H, W]: B samples here, images x F filters in a bank launch
+    const int gplanes = bm.n ? (B / bm.n) * bm.F : B;
+    const int tma_ok = (make_tile_map(&map, img, bm.n ? B / bm.n : B, H, W) &&
+                        make_tile_map(&gmap, gout, gplanes, H, W, kShTileW, kShTileH)) ? 1 : 0;
+    if (grad_img) {
+        sharpen_attrs<true, true>();
+        launch_pdl_smem(sharpen_kernel<true, true>, grid, kThreads, kShSmemBwd, st, map, gmap, tma_ok, img, gout, gy_scratch,
+                        params, ops, H, W, vec, partial, bm, pool);
+    } else {
+        sharpen_attrs<true, false>();
+        launch_pdl_smem(sharpen_kernel<true, false>, grid, kThreads, kShSmemBwd, st, map, gmap, tma_ok, img, gout, nullptr,
+                        params, ops, H, W, vec, partial, bm, pool);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     e = launch_finalize(partial, sharpen_rows(H, W), params, ops, FAMILY_SHARPEN, B, grad_params, bm, st);
     if (e != cudaSuccess) return e;
     if (grad_img) {
-        dim3 g2((W + kAdjW - 1) / kAdjW, (H + kAdjH - 1) / kAdjH, B);
-        launch_pdl(sharpen_adjoint_kernel, g2, kThreads, st, gy_scratch, grad_img, params, ops, H, W);
+        CUtensorMap gmap;
+        const int gtma = make_tile_map(&gmap, gy_scratch, B, H, W) ? 1 : 0;
+        const int gvec = ((W & 3) == 0) && al16(grad_img);
+        launch_pdl(sharpen_adjoint_kernel, grid, kThreads, st, gmap, gtma, gy_scratch, grad_img, params, ops, H, W, gvec);
         e = cudaGetLastError();
     }
     return e;

@@ -33,6 +33,17 @@ for what in "$@"; do
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:pw_chain_fixed -s 4 -c 1 -f -o $OUT/prof_chainfixed_${TAG} \
           python scripts/micro/chain_bench.py --iters 2 > $OUT/${TAG}_ncu_chain.log 2>&1
       tail -3 $OUT/${TAG}_ncu_chain.log;;
+    lag)
+      timeout 600 python scripts/micro/laggard_bench.py 2>&1 | tee $OUT/${TAG}_lag.jsonl;;
+    ncu_lag)
+      # reports stay on the box (64 MiB pull limit): details / raw / source pages come back as text
+      for c in ${NCU_CASES:-shr512 usm4k satp512}; do
+        timeout 600 ncu --set full --clock-control none --import-source on -k regex:"sharpen_kernel|sharpen_adjoint|pw_fwd|pw_bwd" -s ${NCU_SKIP:-3} -c ${NCU_COUNT:-6} -f \
+            -o /tmp/prof_${c} python scripts/micro/laggard_bench.py --iters 1 --only $c > $OUT/${TAG}_ncu_${c}.log 2>&1
+        ncu -i /tmp/prof_${c}.ncu-rep --page details > $OUT/${TAG}_details_${c}.txt 2>&1
+        ncu -i /tmp/prof_${c}.ncu-rep --page raw --csv > $OUT/${TAG}_raw_${c}.csv 2>&1
+        ncu -i /tmp/prof_${c}.ncu-rep --page source --csv > $OUT/${TAG}_source_${c}.csv 2>&1
+        ls -la $OUT/${TAG}_*_${c}.*; done;;
     *) echo "unknown step $what";;
   esac
 done
