@@ -12,8 +12,9 @@
 // filters (frame pixels pass through and interior pixels never read outside the image) and for USM
 // tiles that do not touch the image frame; USM frame tiles (reflect padding) and images whose rows
 // are not 16-byte multiples take the cp.async path, which applies the reflect rule per element.
-// Each thread then produces a 4x2 block per plane from registers (separable 5-tap passes for USM),
-// so HBM sees ~24 B/px forward and ~24 B/px backward; halo re-reads by neighbouring CTAs hit L2.
+// Each thread then produces a 4x2 block per plane from registers as packed fp32 pairs (separable 5-tap
+// passes for USM), so HBM sees ~24 B/px forward and ~24 B/px backward; halo re-reads by neighbouring CTAs
+// hit L2.  Backward: the upstream-gradient tile rides on a second TMA copy into shared memory.
 #include <cstring>
 #include <cstring>
 
@@ -120,72 +121,6 @@ __device__ __forceinline__ void load_consts(const float* __restrict__ params, in
         derive_consts(op, raw, c);
         for (int k = 0; k < kConst; ++k) sc[k] = c[k];
     }
-}
-
-// blur (and optionally d blur / d sigma) of a 4x2 block for one plane.
-//   sm: plane base, SW: row stride, COFF: smem column of tile column 0; (bx, by): block origin in the tile.
-template <bool USM, bool WITH_D, bool FRAME, int SW, int COFF>
-__device__ __forceinline__ void block_blur(const float* sm, int bx, int by, const float* sc, int gx0, int gy0, int H,
-                                           int W, float (&xc)[2][4], float (&blur)[2][4], float (&dblur)[2][4]) {
-    if (USM) {
-        float hk[6][4], hd[6][4];
-        const float k0 = sc[0], k1 = sc[1], k2 = sc[2];
-        const float d0 = sc[5], d1 = sc[6], d2 = sc[7];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = sm[(by + r) * SW + bx + COFF - 2 + i];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float e2 = v[i] + v[i + 4], e1 = v[i + 1] + v[i + 3], e0 = v[i + 2];
-                hk[r][i] = fmaf(k0, e2, fmaf(k1, e1, k2 * e0));
-                if (WITH_D) hd[r][i] = fmaf(d0, e2, fmaf(d1, e1, d2 * e0));
-                if (r >= 2 && r < 4) xc[r - 2][i] = e0;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float e2 = hk[r][i] + hk[r + 4][i], e1 = hk[r + 1][i] + hk[r + 3][i], e0 = hk[r + 2][i];
-                blur[r][i] = fmaf(k0, e2, fmaf(k1, e1, k2 * e0));
-                if (WITH_D) {
-                    const float f2 = hd[r][i] + hd[r + 4][i], f1 = hd[r + 1][i] + hd[r + 3][i], f0 = hd[r + 2][i];
-                    dblur[r][i] = fmaf(d0, e2, fmaf(d1, e1, d2 * e0)) + fmaf(k0, f2, fmaf(k1, f1, k2 * f0));
-                }
-            }
-    } else {
-        const float a = 1.0f / 13.0f, bc = 5.0f / 13.0f;
-        float hs[4][4], ctr[4][4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            float v[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) v[i] = sm[(by + 1 + r) * SW + bx + COFF - 1 + i];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { hs[r][i] = (v[i] + v[i + 1]) + v[i + 2]; ctr[r][i] = v[i + 1]; }
-        }
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float x = ctr[r + 1][i];
-                const float ring = (hs[r][i] + hs[r + 2][i]) + (hs[r + 1][i] - x);
-                xc[r][i] = x;
-                blur[r][i] = fmaf(a, ring, bc * x);
-                if (FRAME) {  // only tiles that touch the image frame pay for the pass-through test
-                    const int gx = gx0 + i, gy = gy0 + r;
-                    if ((gx == 0) || (gy == 0) || (gx == W - 1) || (gy == H - 1)) blur[r][i] = x;
-                }
-                if (WITH_D) dblur[r][i] = 0.f;
-            }
-    }
-}
-
-__device__ __forceinline__ float sharpen_value(int op, float x, float blur, float f) {
-    if (op == AISP_OP_SHARPEN) return x * f + blur * (1.0f - f);
-    return x + (x - blur) * f;  // SHARPEN_V2 and USM
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -545,21 +480,28 @@ sharpen_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_c
     const float* scs = sc[pos];
     const float f = (op == AISP_OP_USM) ? scs[10] : scs[0];
     float y[3][2][4];
+    {   // same packed-pair bodies (and therefore the same bits) as sharpen_kernel
+        const unsigned fbits = (op != AISP_OP_USM && frame_tile) ? frame_bits(gx0, gy0, H, W) : 0u;
+        const f32x2 f2v = splat2(f), omf = splat2(1.0f - f), zero2 = splat2(0.f);
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        float xc[2][4], blur[2][4], dblur[2][4];
-        const float* pl = sm + ch * kSmH * kCpW;
-        if (op == AISP_OP_USM)
-            block_blur<true, false, false, kCpW, kColOff>(pl, bx, by, scs, gx0, gy0, H, W, xc, blur, dblur);
-        else if (frame_tile)
-            block_blur<false, false, true, kCpW, kColOff>(pl, bx, by, scs, gx0, gy0, H, W, xc, blur, dblur);
-        else
-            block_blur<false, false, false, kCpW, kColOff>(pl, bx, by, scs, gx0, gy0, H, W, xc, blur, dblur);
+        for (int ch = 0; ch < 3; ++ch) {
+            f32x2 xc[2][2], blur[2][2], dblur[2][2];
+            const float* pl = sm + ch * kSmH * kCpW + by * kCpW + bx + kColOff;
+            if (op == AISP_OP_USM) usm_block2<false>(pl, scs, xc, blur, dblur);
+            else if (frame_tile) box3_block2<true>(pl, fbits, xc, blur);
+            else box3_block2<false>(pl, fbits, xc, blur);
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+            for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                y[ch][r][i] = clip01(fmaf(0.f, xc[r][i], sharpen_value(op, xc[r][i], blur[r][i], f)));
+                for (int q = 0; q < 2; ++q) {
+                    const f32x2 x = xc[r][q];
+                    const f32x2 v = (op == AISP_OP_SHARPEN) ? add2(mul2(x, f2v), mul2(blur[r][q], omf))
+                                                            : add2(x, mul2(sub2(x, blur[r][q]), f2v));
+                    const f32x2 yy = fma2(zero2, x, v);
+                    y[ch][r][2 * q] = clip01(lo2(yy));
+                    y[ch][r][2 * q + 1] = clip01(hi2(yy));
+                }
+        }
     }
     // epilogue: steps pos+1 .. len-1 on the thread's own outputs
     for (int k = pos + 1; k < len; ++k) {
