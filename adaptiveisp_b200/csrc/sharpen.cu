@@ -10,8 +10,10 @@
 // (measured: x0-2 raises an illegal-instruction fault) --, completion on an mbarrier): a single thread issues it, no warp spends instructions on
 // addresses, and out-of-bounds halo elements arrive as zeros.  That is exactly right for the 3x3
 // filters (frame pixels pass through and interior pixels never read outside the image) and for USM
-// tiles that do not touch the image frame; USM frame tiles (reflect padding) and images whose rows
-// are not 16-byte multiples take the cp.async path, which applies the reflect rule per element.
+// tiles whose halo stays inside the image; a USM tile whose halo leaves it (reflect padding) copies the
+// few out-of-image columns / rows from their mirror positions inside the same tile after the copy has
+// landed (usm_reflect_fixup); images whose rows are not 16-byte multiples take the cp.async path, which
+// applies the reflect rule per element.
 // Each thread then produces a 4x2 block per plane from registers as packed fp32 pairs (separable 5-tap
 // passes for USM), so HBM sees ~24 B/px forward and ~24 B/px backward; halo re-reads by neighbouring CTAs
 // hit L2.  Backward: the upstream-gradient tile rides on a second TMA copy into shared memory.
@@ -109,6 +111,34 @@ __device__ __forceinline__ void stage_tile_cp(const float* __restrict__ img, flo
         }
         if (lane < 4) cp_async4(sm + (ch * kSmH + row) * kCpW + 4 + hc, src + hx);
     }
+}
+
+// Reflect padding on top of a TMA-staged tile (isp/sharpen.py:76-78, F.pad(mode='reflect') by 2): TMA zero-fills the
+// halo elements that lie outside the image; the (at most two) columns and rows beyond each image edge are then copied
+// from their mirror positions, which the same tile holds -- columns first, then whole rows (so corners come out right).
+// Called by every thread of the CTA after the tile has landed; ends with a barrier.
+__device__ __forceinline__ void usm_reflect_fixup(float* sm, int x0, int y0, int H, int W) {
+    const int xs = x0 - kColOff, ys = y0 - kHalo;            // image coordinates of staged column 0 / row 0
+    // columns x in {-2, -1, W, W+1}
+    for (int e = threadIdx.x; e < 3 * kSmH * 4; e += kThreads) {
+        const int which = e & 3, rowp = e >> 2;              // rowp = plane * kSmH + row
+        const int x = (which < 2) ? which - 2 : W + which - 2;
+        const int src = (x < 0) ? -x : 2 * (W - 1) - x;
+        const int cx = x - xs, cs = src - xs;
+        if (cx >= 0 && cx < kCpW && cs >= 0 && cs < kCpW && src >= 0 && src < W) sm[rowp * kCpW + cx] = sm[rowp * kCpW + cs];
+    }
+    __syncthreads();
+    // rows y in {-2, -1, H, H+1}
+    for (int e = threadIdx.x; e < 3 * 4 * kCpW; e += kThreads) {
+        const int col = e % kCpW, t = e / kCpW;
+        const int which = t & 3, pl = t >> 2;
+        const int y = (which < 2) ? which - 2 : H + which - 2;
+        const int src = (y < 0) ? -y : 2 * (H - 1) - y;
+        const int ry = y - ys, rs = src - ys;
+        if (ry >= 0 && ry < kSmH && rs >= 0 && rs < kSmH && src >= 0 && src < H)
+            sm[(pl * kSmH + ry) * kCpW + col] = sm[(pl * kSmH + rs) * kCpW + col];
+    }
+    __syncthreads();
 }
 
 __device__ __forceinline__ void load_consts(const float* __restrict__ params, int b, int op, float* sc /*smem*/) {
@@ -299,14 +329,33 @@ __device__ __forceinline__ void sharpen_tile(const float* tile, const float* gti
     acc[1] = lo2(acc1) + hi2(acc1);
 }
 
-// dynamic shared memory of sharpen_kernel: image tile + halo | upstream-gradient tile (backward) | constants | reduction rows
+// dynamic shared memory of sharpen_kernel: image tile + halo | upstream-gradient tile (backward) | constants | barrier.
+// 57,296 bytes in the backward: FOUR CTAs per SM fit (4 x (57,296 + 1 KB reserved) <= 228 KB), which is what the
+// one-shot CTA (load -> wait -> compute -> reduce) needs to keep enough tiles in flight; the reduction rows reuse the
+// image tile once every thread is done with it, and only the 16 constants the sharpen family reads are kept.
 constexpr int kGoFloats = 3 * kShTileH * kShTileW;                        // 24 KB
 constexpr unsigned kGoBytes = kGoFloats * sizeof(float);
-constexpr size_t kShSmemFwd = (size_t)(kSmFloats + kConst) * sizeof(float) + 16;
-constexpr size_t kShSmemBwd = (size_t)(kSmFloats + kGoFloats + kConst + kWarps * AISP_ACC_STRIDE) * sizeof(float) + 16;
+constexpr int kShConst = 16;
+constexpr size_t kShSmemFwd = (size_t)(kSmFloats + kShConst) * sizeof(float) + 16;
+constexpr size_t kShSmemBwd = (size_t)(kSmFloats + kGoFloats + kShConst) * sizeof(float) + 16;
+static_assert(kShSmemBwd <= 57344, "four backward CTAs per SM");
+static_assert(kWarps * AISP_ACC_STRIDE <= kSmFloats, "reduction rows alias the image tile");
+
+// constants of one sample into shared memory (thread 0; the caller synchronises)
+__device__ __forceinline__ void load_consts16(const float* __restrict__ params, int b, int op, float* sc /*smem, kShConst*/) {
+    if (threadIdx.x == 0) {
+        float raw[kConst];
+        for (int k = 0; k < AISP_PSTRIDE; ++k) raw[k] = params[(size_t)b * AISP_PSTRIDE + k];
+        for (int k = AISP_PSTRIDE; k < kConst; ++k) raw[k] = 0.f;
+        float c[kConst];
+        for (int k = 0; k < kConst; ++k) c[k] = 0.f;
+        derive_consts(op, raw, c);
+        for (int k = 0; k < kShConst; ++k) sc[k] = c[k];
+    }
+}
 
 template <bool BWD, bool WRITE_GY>
-__global__ void __launch_bounds__(kThreads, BWD ? 3 : 4)
+__global__ void __launch_bounds__(kThreads, 4)
 sharpen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap gmap, int tma_ok,
                const float* __restrict__ img, const float* __restrict__ gout, float* __restrict__ out,
                const float* __restrict__ params, const int32_t* __restrict__ ops, int H, int W, int vec,
@@ -315,9 +364,9 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     extern __shared__ __align__(128) float shsm[];
     float* sm = shsm;                                            // [3][kSmH][kCpW]
     float* gs = shsm + kSmFloats;                                // [3][kShTileH][kShTileW]  (backward, TMA path)
-    float* sc = shsm + kSmFloats + (BWD ? kGoFloats : 0);        // [kConst]
-    float* red = sc + kConst;                                    // [kWarps][AISP_ACC_STRIDE]  (backward)
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(red + (BWD ? kWarps * AISP_ACC_STRIDE : 0));
+    float* sc = shsm + kSmFloats + (BWD ? kGoFloats : 0);        // [kShConst]
+    float* red = shsm;                                           // [kWarps][AISP_ACC_STRIDE]: the image tile's memory, after use
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(sc + kShConst);
     const int b = bank_sample(bm, blockIdx.z);   // filter-bank launches: see BankMap
     const int op = sample_op(ops, bm, b);
     if (!is_sharpen(op)) return;
@@ -328,7 +377,7 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     // reflecting cp.async path as soon as its 2-px HALO leaves the image (H = y0 + 17 puts halo row
     // y0 + 17 == H outside although the tile itself ends one row short of the frame)
     const bool usm_halo_out = (x0 < kHalo) || (y0 < kHalo) || (x0 + kShTileW + kHalo > W) || (y0 + kShTileH + kHalo > H);
-    const bool use_tma = tma_ok && !(op == AISP_OP_USM && usm_halo_out);
+    const bool use_tma = tma_ok != 0;   // USM tiles whose halo leaves the image: zero fill now, mirrored below
     // the upstream gradient rides on TMA whenever the launch can (its zero fill makes rows / columns past the
     // image contribute nothing); tma_ok covers both maps
     const bool g_tma = BWD && tma_ok;
@@ -342,7 +391,7 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         }
         // one wave ahead: the tiles that a CTA scheduled ~one machine-fill later will load go to L2 now
         if (threadIdx.x == 32) {
-            const int ahead = 148 * (BWD ? 3 : 4);
+            const int ahead = 148 * 4;
             int lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + ahead;
             const int px = lin % gridDim.x;
             lin /= gridDim.x;
@@ -357,7 +406,7 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         }
     }
     if (!use_tma) stage_tile_cp(img + (size_t)(b / bm.F) * 3 * H * W, sm, H, W, x0, y0, vec != 0);
-    load_consts(params, b, op, sc);
+    load_consts16(params, b, op, sc);
 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int bx = tx * 4, by = ty * 2;
@@ -366,6 +415,7 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     if (!use_tma) cp_async_wait_all();
     if (tma_ok) mbar_wait(bar, 0);
     __syncthreads();
+    if (use_tma && op == AISP_OP_USM && usm_halo_out) usm_reflect_fixup(sm, x0, y0, H, W);   // CTA-uniform
     float acc[2] = {0.f, 0.f};
     // CTA-uniform specialisation: whole tile inside the image with 128-bit accesses (no per-row / per-column
     // tests), and the stencil kind (5x5 USM, 3x3 away from the frame, 3x3 on the frame)
@@ -388,6 +438,7 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     if (BWD) {
         const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
         const int ntiles = gridDim.x * gridDim.y;
+        __syncthreads();   // every thread is done with the image tile: its memory now holds the reduction rows
         block_reduce_store<2>(acc, red, partial + ((size_t)b * ntiles + tile_id) * AISP_ACC_STRIDE);
     }
 }
@@ -443,7 +494,7 @@ sharpen_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_c
     const int op = ops[(size_t)b * S + pos];
     const bool frame_tile = (x0 == 0) || (y0 == 0) || (x0 + kShTileW >= W) || (y0 + kShTileH >= H);
     const bool usm_halo_out = (x0 < kHalo) || (y0 < kHalo) || (x0 + kShTileW + kHalo > W) || (y0 + kShTileH + kHalo > H);
-    const bool use_tma = J.tma_ok && !(op == AISP_OP_USM && usm_halo_out);
+    const bool use_tma = J.tma_ok != 0;
     if (use_tma) {
         if (threadIdx.x == 0) mbar_init(&bar, 1);
         __syncthreads();
@@ -458,6 +509,7 @@ sharpen_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_c
     if (use_tma) mbar_wait(&bar, 0);
     else cp_async_wait_all();
     __syncthreads();
+    if (use_tma && op == AISP_OP_USM && usm_halo_out) usm_reflect_fixup(sm, x0, y0, H, W);   // CTA-uniform
 
     // prologue: steps 0 .. pos-1 on every staged pixel (tile + halo), in place
     if (pos > 0) {

@@ -27,11 +27,14 @@ for what in "$@"; do
       timeout 600 python scripts/micro/chain_bench.py 2>&1 | tee $OUT/${TAG}_chain.jsonl;;
     chain_ab)
       rm -f $OUT/${TAG}_chain_ab.jsonl
-      for c in 13 14 23 24; do echo "cfg $c" | tee -a $OUT/${TAG}_chain_ab.jsonl
+      for c in 31 32 21 22; do echo "cfg $c" | tee -a $OUT/${TAG}_chain_ab.jsonl
         AISP_CHAIN_CFG=$c timeout 600 python scripts/micro/chain_bench.py --cases 1 2>&1 | tee -a $OUT/${TAG}_chain_ab.jsonl; done;;
     ncu_chain)
-      timeout 600 ncu --set full --clock-control none --import-source on -k regex:pw_chain_fixed -s 4 -c 1 -f -o $OUT/prof_chainfixed_${TAG} \
-          python scripts/micro/chain_bench.py --iters 2 > $OUT/${TAG}_ncu_chain.log 2>&1
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:pw_chain_fixed -s 4 -c 1 -f -o /tmp/prof_chainfixed \
+          python scripts/micro/chain_bench.py --iters 2 --cases 1 > $OUT/${TAG}_ncu_chain.log 2>&1
+      ncu -i /tmp/prof_chainfixed.ncu-rep --page details > $OUT/${TAG}_details_chain.txt 2>&1
+      ncu -i /tmp/prof_chainfixed.ncu-rep --page raw --csv > $OUT/${TAG}_raw_chain.csv 2>&1
+      ncu -i /tmp/prof_chainfixed.ncu-rep --page source --csv > $OUT/${TAG}_source_chain.csv 2>&1
       tail -3 $OUT/${TAG}_ncu_chain.log;;
     lag)
       timeout 600 python scripts/micro/laggard_bench.py 2>&1 | tee $OUT/${TAG}_lag.jsonl;;

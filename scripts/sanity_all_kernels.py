@@ -61,6 +61,15 @@ for (B, H, W) in [(3, 37, 53), (2, 48, 64), (1, 9, 130)]:
     Pg = [ph.params.clone().requires_grad_(True) for ph in plan.phases]
     (apply_plan(img.clone().requires_grad_(True), plan, Pg) * g).sum().backward()
     AF.value_stats(AF.block_mean(torch.rand((B, 3, 64, 96), device=dev), (16, 24)))
+    # synthetic-RAW noise (in-kernel Philox and injected normals), bare NLM modules incl. NonLocalMeansParam
+    from adaptiveisp_b200 import unprocess as U, denoise as D
+    U.add_read_and_shot_noise(img.clamp(0, 1), [0.01] * B, [1e-4] * B, gain=[0.2] * B, seed=3)
+    U.add_read_and_shot_noise(img.clamp(0, 1), 0.01, 1e-4, z=torch.randn_like(img))
+    hh = torch.full((B, 1, 1, 1), 0.3, device=dev, requires_grad=True)
+    (D.NonLocalMeansGray()(img, hh).sum() + D.NonLocalMeans()(img, hh).sum()).backward()
+    if H >= 12 and W >= 12:
+        pm = D.NonLocalMeansParam(0.3).to(dev)
+        pm(img).sum().backward()
 from adaptiveisp_b200 import filters as Fm
 from adaptiveisp_b200.config import make_cfg
 cfg = make_cfg(feature_extractor_dims=64, fc1_size=16)
