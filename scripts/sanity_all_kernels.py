@@ -66,9 +66,9 @@ for (B, H, W) in [(3, 37, 53), (2, 48, 64), (1, 9, 130)]:
     U.add_read_and_shot_noise(img.clamp(0, 1), [0.01] * B, [1e-4] * B, gain=[0.2] * B, seed=3)
     U.add_read_and_shot_noise(img.clamp(0, 1), 0.01, 1e-4, z=torch.randn_like(img))
     hh = torch.full((B, 1, 1, 1), 0.3, device=dev, requires_grad=True)
-    (D.NonLocalMeansGray()(img, hh).sum() + D.NonLocalMeans()(img, hh).sum()).backward()
-    if H >= 12 and W >= 12:
-        pm = D.NonLocalMeansParam(0.3).to(dev)
+    (D.NonLocalMeansGray(11, 5)(img, hh).sum() + D.NonLocalMeans(11, 5)(img, hh).sum()).backward()
+    if H >= 5 and W >= 5:
+        pm = D.NonLocalMeansParam(0.3, search_window_size=7).to(dev)
         pm(img).sum().backward()
 from adaptiveisp_b200 import filters as Fm
 from adaptiveisp_b200.config import make_cfg
