@@ -514,6 +514,12 @@ finalize_kernel(const float* __restrict__ partial, int nrows, const float* __res
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (family == FAMILY_SHARPEN) {   // a sharpen scratch row holds (sum0, sum1, 0, 0) per warp: see sharpen_kernel
+            double f0 = 0.0, f1 = 0.0;
+            for (int w = 0; w < kWarps; ++w) { f0 += tot[4 * w]; f1 += tot[4 * w + 1]; }
+            tot[0] = f0;
+            tot[1] = f1;
+        }
         derive_consts(op, raw, c);
         float gp[AISP_PSTRIDE];
         finalize_grads(op, tot, c, raw, gp);

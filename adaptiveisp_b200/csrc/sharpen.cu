@@ -50,6 +50,10 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
     const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile(
@@ -331,15 +335,15 @@ __device__ __forceinline__ void sharpen_tile(const float* tile, const float* gti
 
 // dynamic shared memory of sharpen_kernel: image tile + halo | upstream-gradient tile (backward) | constants | barrier.
 // 57,296 bytes in the backward: FOUR CTAs per SM fit (4 x (57,296 + 1 KB reserved) <= 228 KB), which is what the
-// one-shot CTA (load -> wait -> compute -> reduce) needs to keep enough tiles in flight; the reduction rows reuse the
-// image tile once every thread is done with it, and only the 16 constants the sharpen family reads are kept.
+// one-shot CTA (load -> wait -> compute -> reduce) needs to keep enough tiles in flight; the reduction needs no shared
+// memory (per-warp entries of the scratch row) and only the 16 constants the sharpen family reads are kept.
 constexpr int kGoFloats = 3 * kShTileH * kShTileW;                        // 24 KB
 constexpr unsigned kGoBytes = kGoFloats * sizeof(float);
 constexpr int kShConst = 16;
 constexpr size_t kShSmemFwd = (size_t)(kSmFloats + kShConst) * sizeof(float) + 16;
 constexpr size_t kShSmemBwd = (size_t)(kSmFloats + kGoFloats + kShConst) * sizeof(float) + 16;
 static_assert(kShSmemBwd <= 57344, "four backward CTAs per SM");
-static_assert(kWarps * AISP_ACC_STRIDE <= kSmFloats, "reduction rows alias the image tile");
+static_assert(kWarps * 4 == AISP_ACC_STRIDE, "one scratch row holds four floats per warp");
 
 // constants of one sample into shared memory (thread 0; the caller synchronises)
 __device__ __forceinline__ void load_consts16(const float* __restrict__ params, int b, int op, float* sc /*smem, kShConst*/) {
@@ -365,7 +369,6 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     float* sm = shsm;                                            // [3][kSmH][kCpW]
     float* gs = shsm + kSmFloats;                                // [3][kShTileH][kShTileW]  (backward, TMA path)
     float* sc = shsm + kSmFloats + (BWD ? kGoFloats : 0);        // [kShConst]
-    float* red = shsm;                                           // [kWarps][AISP_ACC_STRIDE]: the image tile's memory, after use
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(sc + kShConst);
     const int b = bank_sample(bm, blockIdx.z);   // filter-bank launches: see BankMap
     const int op = sample_op(ops, bm, b);
@@ -382,7 +385,9 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     // image contribute nothing); tma_ok covers both maps
     const bool g_tma = BWD && tma_ok;
     if (tma_ok) {
-        if (threadIdx.x == 0) mbar_init(bar, 1);
+        // two arrivals complete the phase: the TMA issue (with its byte count) and the constants (below), so that a
+        // thread that has seen the phase flip may read tile, gradient tile AND constants -- no CTA barrier after the load
+        if (threadIdx.x == 0) mbar_init(bar, 2);
         __syncthreads();
         if (threadIdx.x == 0) {
             mbar_expect_tx(bar, (use_tma ? kTmaBytes : 0u) + (g_tma ? kGoBytes : 0u));
@@ -407,15 +412,22 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     }
     if (!use_tma) stage_tile_cp(img + (size_t)(b / bm.F) * 3 * H * W, sm, H, W, x0, y0, vec != 0);
     load_consts16(params, b, op, sc);
+    if (tma_ok && threadIdx.x == 0) mbar_arrive(bar);   // release: the constants are written
 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int bx = tx * 4, by = ty * 2;
     const int gx0 = x0 + bx, gy0 = y0 + by;
     const bool vec_ok = vec && (gx0 + 3 < W);  // vec: W % 4 == 0 and 16B-aligned global pointers
-    if (!use_tma) cp_async_wait_all();
-    if (tma_ok) mbar_wait(bar, 0);
-    __syncthreads();
-    if (use_tma && op == AISP_OP_USM && usm_halo_out) usm_reflect_fixup(sm, x0, y0, H, W);   // CTA-uniform
+    if (tma_ok) {
+        mbar_wait(bar, 0);
+    } else {
+        cp_async_wait_all();
+        __syncthreads();
+    }
+    if (use_tma && op == AISP_OP_USM && usm_halo_out) {   // CTA-uniform
+        __syncthreads();                                  // every thread has seen the tile before cells are rewritten
+        usm_reflect_fixup(sm, x0, y0, H, W);
+    }
     float acc[2] = {0.f, 0.f};
     // CTA-uniform specialisation: whole tile inside the image with 128-bit accesses (no per-row / per-column
     // tests), and the stencil kind (5x5 USM, 3x3 away from the frame, 3x3 on the frame)
@@ -436,10 +448,18 @@ sharpen_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     }
 #undef AISP_SHARPEN_TILE
     if (BWD) {
+        // no CTA barrier: every warp reduces its two sums by shuffles and owns four floats (two sums, two zeros) of the
+        // tile's scratch row; finalize_kernel adds the eight warps' entries in fixed order (FAMILY_SHARPEN)
         const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
         const int ntiles = gridDim.x * gridDim.y;
-        __syncthreads();   // every thread is done with the image tile: its memory now holds the reduction rows
-        block_reduce_store<2>(acc, red, partial + ((size_t)b * ntiles + tile_id) * AISP_ACC_STRIDE);
+        float a0 = acc[0], a1 = acc[1];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        }
+        if (tx < 4)
+            partial[((size_t)b * ntiles + tile_id) * AISP_ACC_STRIDE + ty * 4 + tx] = (tx == 0) ? a0 : ((tx == 1) ? a1 : 0.f);
     }
 }
 
