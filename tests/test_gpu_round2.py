@@ -338,7 +338,9 @@ def test_nan_batch_trips_the_pool_refill_guard(F, cfg, dev):
 # ----------------------------------------------------------------------------------------------
 # 5. USM: a tile whose 2-px halo leaves the image although the tile itself does not touch the frame
 # ----------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("size", [(1, 33, 260), (1, 49, 512), (2, 17, 384), (1, 34, 260), (1, 35, 516)])
+@pytest.mark.parametrize("size", [(1, 33, 260), (1, 49, 512), (2, 17, 384), (1, 34, 260), (1, 35, 516),
+                                  # one tile holding both frames of an axis, images smaller than the halo box, W % 4 != 0
+                                  (1, 3, 4), (1, 5, 8), (2, 18, 132), (1, 16, 128), (1, 4, 128), (1, 7, 9), (1, 19, 131)])
 def test_usm_halo_leaves_image_on_tma_path(F, cfg, dev, size):
     """H % 16 == 1 with W % 4 == 0 and W > 256: the last-but-one tile row ends one row short of the frame
     while its halo row y0 + 17 == H is outside; reflect padding (isp/sharpen.py:76-78) must apply there
@@ -357,6 +359,37 @@ def test_usm_halo_leaves_image_on_tma_path(F, cfg, dev, size):
     err = (yd.detach().cpu() - yc.detach()).abs()
     assert float(err.max()) <= OUT_ATOL, f"worst row {int(err.amax(dim=(0, 1, 3)).argmax())} of {H}"
     assert_grad(pd.grad.cpu().numpy(), pc.grad.numpy(), GRAD_RTOL, "USM d/d(sigma, amount)")
+    assert rel_err(xd.grad.cpu().numpy(), xc.grad.numpy()) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("size", [(1, 3, 4), (1, 5, 8), (2, 18, 132), (1, 16, 128), (1, 33, 260), (1, 7, 9), (2, 34, 516)])
+@pytest.mark.parametrize("op", ["SHARPEN", "SHARPEN_V2"])
+def test_sharpen_3x3_frame_and_small_sizes(dev, op, size):
+    """3x3 filters on the packed-pair kernels: frame pixels pass x through (isp/sharpen.py:105-142), tiles that hold
+    both frames of an axis, images narrower than a tile, the scalar (W % 4 != 0) path; forward, d/df, d/d img
+    (transposed stencil with the frame pixels' gradient masked out of the blur)."""
+    from adaptiveisp_b200 import functional as AF
+    opc = getattr(O, "OP_" + op)
+    B, H, W = size
+    img = cases.edge_image(B, H, W, seed=H + W, in_range=True)
+    p = torch.tensor([[1.7], [0.4]])[:B]
+    g = cases.grad_out(img.shape, W)
+    # knife-edge pixels: on the k/255 lattice of sample 0 the pre-clip value can be EXACTLY 0 or 1 in exact arithmetic
+    # (e.g. 2.7 x = 1.7 blur); which side of the clamp it lands on in fp32 depends on the summation order of the 3x3
+    # convolution (oneDNN's, in the reference), so the gradient mask of such a pixel is not defined by the arithmetic.
+    # They are found in float64 and taken out of the upstream gradient.
+    x64, f64 = img.double(), p.double()[:, :, None, None]
+    b64 = O._blur3x3_keep_border(x64)
+    y64 = x64 * f64 + b64 * (1.0 - f64) if op == "SHARPEN" else x64 + (x64 - b64) * f64
+    g = g * ((y64.abs() > 1e-6) & ((y64 - 1.0).abs() > 1e-6)).float()
+    xc, pc = img.clone().requires_grad_(True), p.clone().requires_grad_(True)
+    yc = O.forward(opc, xc, pc)
+    (yc * g).sum().backward()
+    xd, pd = img.to(dev).requires_grad_(True), p.to(dev).requires_grad_(True)
+    yd = AF.apply_filter(xd, pd, opc, True)
+    (yd * g.to(dev)).sum().backward()
+    assert float((yd.detach().cpu() - yc.detach()).abs().max()) <= OUT_ATOL
+    assert_grad(pd.grad.cpu().numpy(), pc.grad.numpy(), GRAD_RTOL, op + " d/df")
     assert rel_err(xd.grad.cpu().numpy(), xc.grad.numpy()) <= GRAD_RTOL
 
 
