@@ -156,18 +156,8 @@ __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
     return r;
 }
 __device__ __forceinline__ f32x2 splat2(float v) { return pack2(v, v); }
-__device__ __forceinline__ float lo2(f32x2 v) {
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-    (void)hi;
-    return lo;
-}
-__device__ __forceinline__ float hi2(f32x2 v) {
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-    (void)lo;
-    return hi;
-}
+__device__ __forceinline__ float lo2(f32x2 v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
+__device__ __forceinline__ float hi2(f32x2 v) { return __uint_as_float((unsigned)(v >> 32)); }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
     f32x2 r;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
@@ -188,6 +178,14 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
+// Sum / difference that must NOT be contracted with a multiply feeding it: ptxas (CUDA 12.9) fuses mul.rn.f32x2 +
+// add.rn.f32x2 into FFMA2 despite the explicit .rn and -fmad=false (it honours both for the scalar forms), and it
+// also folds a literal x * 1.0 + y back into that pattern.  Written as x * ONE + y with ONE read from constant memory
+// (opaque to ptxas) the sum is the same correctly rounded value, costs the same one instruction (FFMA2 with a uniform
+// broadcast operand), and has no free multiply to contract.  Checked in SASS: FMUL2, FMUL2, FFMA2 -- not FMUL2, FFMA2.
+static __constant__ float kOpaqueOne[2] = {1.0f, -1.0f};
+__device__ __forceinline__ f32x2 add2_sep(f32x2 x, f32x2 y) { return fma2(x, splat2(kOpaqueOne[0]), y); }
+__device__ __forceinline__ f32x2 sub2_sep(f32x2 x, f32x2 y) { return fma2(y, splat2(kOpaqueOne[1]), x); }   // x - y
 __device__ __forceinline__ f32x2 lds2(const float* p) {   // 8-byte aligned pair from shared memory
     return *reinterpret_cast<const f32x2*>(p);
 }

@@ -244,15 +244,128 @@ __device__ __forceinline__ void fwd_px(int op, const float* __restrict__ c, floa
     R = yr; G = yg; B = yb;
 }
 
+// Two pixels at a time as packed fp32 (FMUL2 / FADD2 / FFMA2: one issue slot per two results).  Lane-wise
+// this is fwd_px: the same operations in the same order with the same (IEEE round-to-nearest) rounding, so
+// the results are bit-identical; MUFU, min / max, compares and the HSV round trip stay per lane.  A forward
+// pass keeps no accumulators, so packing costs no registers.
+__device__ __forceinline__ f32x2 lum_isp2(f32x2 r, f32x2 g, f32x2 b) {
+    return add2_sep(add2_sep(mul2(splat2(0.27f), r), mul2(splat2(0.67f), g)), mul2(splat2(0.06f), b));
+}
+__device__ __forceinline__ f32x2 curve8_2(f32x2 x, const float* c, int stride) {
+    f32x2 acc = splat2(0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const f32x2 u = (k == 0) ? pack2(clip01(lo2(x) * 8.0f), clip01(hi2(x) * 8.0f))
+                                 : pack2(__saturatef(fmaf(lo2(x), 8.0f, -(float)k)), __saturatef(fmaf(hi2(x), 8.0f, -(float)k)));
+        acc = fma2(u, splat2(c[k * stride]), acc);
+    }
+    return acc;
+}
+
+template <bool POISON>
+__device__ __forceinline__ void fwd_px2(int op, const float* __restrict__ c, f32x2& R, f32x2& G, f32x2& B) {
+    const f32x2 r = R, g = G, b = B;
+    f32x2 yr = r, yg = g, yb = b;
+    switch (op) {
+    case AISP_OP_EXPOSURE: {
+        const f32x2 s = splat2(c[0]);
+        yr = mul2(r, s); yg = mul2(g, s); yb = mul2(b, s);
+        break;
+    }
+    case AISP_OP_GAMMA: {
+        const f32x2 p = splat2(c[0]);
+        const f32x2 tr = mul2(p, pack2(lg2_mufu(max_nan(lo2(r), 0.001f)), lg2_mufu(max_nan(hi2(r), 0.001f))));
+        const f32x2 tg = mul2(p, pack2(lg2_mufu(max_nan(lo2(g), 0.001f)), lg2_mufu(max_nan(hi2(g), 0.001f))));
+        const f32x2 tb = mul2(p, pack2(lg2_mufu(max_nan(lo2(b), 0.001f)), lg2_mufu(max_nan(hi2(b), 0.001f))));
+        yr = pack2(ex2_mufu(lo2(tr)), ex2_mufu(hi2(tr)));
+        yg = pack2(ex2_mufu(lo2(tg)), ex2_mufu(hi2(tg)));
+        yb = pack2(ex2_mufu(lo2(tb)), ex2_mufu(hi2(tb)));
+        break;
+    }
+    case AISP_OP_WB: {
+        yr = mul2(r, splat2(c[0])); yg = mul2(g, splat2(c[1])); yb = mul2(b, splat2(c[2]));
+        break;
+    }
+    case AISP_OP_CCM: {
+        yr = add2_sep(add2_sep(mul2(r, splat2(c[0])), mul2(g, splat2(c[1]))), mul2(b, splat2(c[2])));
+        yg = add2_sep(add2_sep(mul2(r, splat2(c[3])), mul2(g, splat2(c[4]))), mul2(b, splat2(c[5])));
+        yb = add2_sep(add2_sep(mul2(r, splat2(c[6])), mul2(g, splat2(c[7]))), mul2(b, splat2(c[8])));
+        break;
+    }
+    case AISP_OP_TONE: {
+        const f32x2 sc = splat2(c[8] * 0.125f);
+        yr = mul2(curve8_2(r, c, 1), sc);
+        yg = mul2(curve8_2(g, c, 1), sc);
+        yb = mul2(curve8_2(b, c, 1), sc);
+        break;
+    }
+    case AISP_OP_COLOR: {
+        yr = mul2(curve8_2(r, c + 0, 3), splat2(c[24] * 0.125f));
+        yg = mul2(curve8_2(g, c + 1, 3), splat2(c[25] * 0.125f));
+        yb = mul2(curve8_2(b, c + 2, 3), splat2(c[26] * 0.125f));
+        break;
+    }
+    case AISP_OP_CONTRAST: {
+        const float p = c[0], ip = 1.f - p;
+        const f32x2 l0 = lum_isp2(r, g, b);
+        const float la = clip01(lo2(l0)), lb = clip01(hi2(l0));
+        const f32x2 cl = pack2(-__cosf(AISP_PIF * la) * 0.5f + 0.5f, -__cosf(AISP_PIF * lb) * 0.5f + 0.5f);
+        const f32x2 inv = pack2(1.0f / (la + 1e-6f), 1.0f / (lb + 1e-6f));
+        const f32x2 ip2 = splat2(ip), p2 = splat2(p);
+        yr = add2_sep(mul2(ip2, r), mul2(p2, mul2(mul2(r, inv), cl)));
+        yg = add2_sep(mul2(ip2, g), mul2(p2, mul2(mul2(g, inv), cl)));
+        yb = add2_sep(mul2(ip2, b), mul2(p2, mul2(mul2(b, inv), cl)));
+        break;
+    }
+    case AISP_OP_WNB: {
+        const float p = c[0], ip = 1.f - p;
+        const f32x2 pl = mul2(splat2(p), lum_isp2(r, g, b)), ip2 = splat2(ip);
+        yr = add2_sep(mul2(ip2, r), pl);
+        yg = add2_sep(mul2(ip2, g), pl);
+        yb = add2_sep(mul2(ip2, b), pl);
+        break;
+    }
+    case AISP_OP_SATPLUS: {
+        const float p = c[0], ip = 1.f - p;
+        const float ar = clip01(lo2(r)), ag = clip01(lo2(g)), ab = clip01(lo2(b));
+        const float br = clip01(hi2(r)), bg = clip01(hi2(g)), bb = clip01(hi2(b));
+        float f0r, f0g, f0b, f1r, f1g, f1b;
+        satplus_forward(ar, ag, ab, f0r, f0g, f0b);
+        satplus_forward(br, bg, bb, f1r, f1g, f1b);
+        const f32x2 ip2 = splat2(ip), p2 = splat2(p);
+        yr = add2_sep(mul2(pack2(ar, br), ip2), mul2(pack2(f0r, f1r), p2));
+        yg = add2_sep(mul2(pack2(ag, bg), ip2), mul2(pack2(f0g, f1g), p2));
+        yb = add2_sep(mul2(pack2(ab, bb), ip2), mul2(pack2(f0b, f1b), p2));
+        break;
+    }
+    default: break;
+    }
+    if (POISON) {
+        const f32x2 z = splat2(0.f);
+        yr = fma2(z, r, yr); yg = fma2(z, g, yg); yb = fma2(z, b, yb);
+    }
+    R = yr; G = yg; B = yb;
+}
+
 // NPX pixels of one thread through one filter; the op switch is CTA-uniform and hoisted by the
-// compiler out of the (unrolled) pixel loop.
+// compiler out of the (unrolled) pixel loop.  Even NPX: pixel pairs (2i, 2i+1) go through fwd_px2.
 template <int NPX, bool POISON = true>
 __device__ __forceinline__ void fwd_step(int op, const float* __restrict__ c, float (&R)[NPX], float (&G)[NPX],
                                          float (&B)[NPX]) {
     switch (op) {
 #define AISP_FWD_CASE(OPC)                                                                   \
     case OPC: {                                                                              \
-        _Pragma("unroll") for (int i = 0; i < NPX; ++i) fwd_px<POISON>(OPC, c, R[i], G[i], B[i]); \
+        if constexpr (NPX % 2 == 0) {                                                        \
+            _Pragma("unroll") for (int i = 0; i < NPX; i += 2) {                             \
+                f32x2 r2 = pack2(R[i], R[i + (NPX > 1)]), g2 = pack2(G[i], G[i + (NPX > 1)]), b2 = pack2(B[i], B[i + (NPX > 1)]); \
+                fwd_px2<POISON>(OPC, c, r2, g2, b2);                                         \
+                R[i] = lo2(r2); R[i + (NPX > 1)] = hi2(r2);                                  \
+                G[i] = lo2(g2); G[i + (NPX > 1)] = hi2(g2);                                  \
+                B[i] = lo2(b2); B[i + (NPX > 1)] = hi2(b2);                                  \
+            }                                                                                \
+        } else {                                                                             \
+            _Pragma("unroll") for (int i = 0; i < NPX; ++i) fwd_px<POISON>(OPC, c, R[i], G[i], B[i]); \
+        }                                                                                    \
         break;                                                                               \
     }
         AISP_FWD_CASE(AISP_OP_EXPOSURE)

@@ -280,7 +280,7 @@ __device__ __forceinline__ void sharpen_tile(const float* tile, const float* gti
                 const f32x2 x = xc[r][q];
                 xmb[q] = sub2(x, blur[r][q]);
                 // products rounded, then added, as the reference's ATen expressions are
-                const f32x2 v = (!usm && blend) ? add2(mul2(x, f), mul2(blur[r][q], omf)) : add2(x, mul2(xmb[q], f));
+                const f32x2 v = (!usm && blend) ? add2_sep(mul2(x, f), mul2(blur[r][q], omf)) : add2_sep(x, mul2(xmb[q], f));
                 y[q] = fma2(zero2, x, v);   // 0 * x: the (1 - mask) * img term of the reference's lerp (NaN iff x is inf / NaN)
             }
             if (!BWD) {
@@ -567,8 +567,8 @@ sharpen_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_c
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const f32x2 x = xc[r][q];
-                    const f32x2 v = (op == AISP_OP_SHARPEN) ? add2(mul2(x, f2v), mul2(blur[r][q], omf))
-                                                            : add2(x, mul2(sub2(x, blur[r][q]), f2v));
+                    const f32x2 v = (op == AISP_OP_SHARPEN) ? add2_sep(mul2(x, f2v), mul2(blur[r][q], omf))
+                                                            : add2_sep(x, mul2(sub2(x, blur[r][q]), f2v));
                     const f32x2 yy = fma2(zero2, x, v);
                     y[ch][r][2 * q] = clip01(lo2(yy));
                     y[ch][r][2 * q + 1] = clip01(hi2(yy));
