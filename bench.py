@@ -245,12 +245,14 @@ def pcie_probe(dev, world, barrier, dist, nbytes, reps=4):
     for name, fn in (("h2d", h2d), ("d2h", d2h), ("duplex_per_dir", both)):
         fn()
         torch.cuda.synchronize(dev)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            fn()
-        torch.cuda.synchronize(dev)
-        gbs = nbytes * reps / 1e9 / (time.perf_counter() - t0)
+        gbs = 0.0
+        for _trial in range(3):   # a bound is the best the link did: the host side is shared with other tenants of the box
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize(dev)
+            gbs = max(gbs, nbytes * reps / 1e9 / (time.perf_counter() - t0))
         t = torch.tensor([gbs, -gbs], device=dev)
         if world > 1:
             lo = t.clone()
