@@ -7,8 +7,8 @@
 // CTA <-> (sample, 128x16 tile).  The tile plus a 2-px halo of all three planes is staged in shared
 // memory by ONE TMA bulk-tensor copy (cp.async.bulk.tensor.3d over a [B*3, H, W] tensor map, box
 // 3 x 20 x 136 starting at column x0-4 -- the innermost TMA coordinate must be 16-byte aligned
-// (measured: x0-2 raises an illegal-instruction fault) --, completion on an mbarrier): a single thread issues it, no warp spends instructions on
-// addresses, and out-of-bounds halo elements arrive as zeros.  That is exactly right for the 3x3
+// (measured: x0-2 raises an illegal-instruction fault) --, completion on an mbarrier): a single thread
+// issues it, no warp spends instructions on addresses, and out-of-bounds halo elements arrive as zeros.  That is exactly right for the 3x3
 // filters (frame pixels pass through and interior pixels never read outside the image) and for USM
 // tiles whose halo stays inside the image; a USM tile whose halo leaves it (reflect padding) copies the
 // few out-of-image columns / rows from their mirror positions inside the same tile after the copy has
@@ -17,7 +17,6 @@
 // Each thread then produces a 4x2 block per plane from registers as packed fp32 pairs (separable 5-tap
 // passes for USM), so HBM sees ~24 B/px forward and ~24 B/px backward; halo re-reads by neighbouring CTAs
 // hit L2.  Backward: the upstream-gradient tile rides on a second TMA copy into shared memory.
-#include <cstring>
 #include <cstring>
 
 #include <cuda.h>  // CUtensorMap and enums only; cuTensorMapEncodeTiled is resolved through the runtime
@@ -789,9 +788,6 @@ sharpen_adjoint_kernel(const __grid_constant__ CUtensorMap tmap, int tma_ok, con
     else adjoint_block<false>(sm, sc, op, H, W, gx0, gy0, bx, by, gimg + base, vec_ok);
 }
 
-// ---------------------------------------------------------------------------------------------
-// host-side launchers
-// ---------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------------------
