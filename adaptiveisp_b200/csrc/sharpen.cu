@@ -674,7 +674,7 @@ __device__ __forceinline__ void adjoint_block(const float* sm, const float* sc, 
     // per-thread: does the 4x2 block hold an output that collects mirror taps (USM) ...
     const bool near_x = FRAME && usm && ((gx0 <= 2) || (gx0 + 3 >= W - 3));
     const bool near_y = FRAME && usm && ((gy0 <= 2) || (gy0 + 1 >= H - 3));
-#pragma unroll
+#pragma unroll 1   // rolled: a third of the code (the unrolled kernel stalled on instruction fetch)
     for (int ch = 0; ch < 3; ++ch) {
         const float* pl = sm + ch * kSmH * kCpW + by * kCpW + bx + kColOff - 2;   // 8-byte aligned
         float hrow[6][4], g0[2][4], ctr[2][4];
