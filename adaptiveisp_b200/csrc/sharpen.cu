@@ -674,6 +674,35 @@ __device__ __forceinline__ void adjoint_block(const float* sm, const float* sc, 
     // per-thread: does the 4x2 block hold an output that collects mirror taps (USM) ...
     const bool near_x = FRAME && usm && ((gx0 <= 2) || (gx0 + 3 >= W - 3));
     const bool near_y = FRAME && usm && ((gy0 <= 2) || (gy0 + 1 >= H - 3));
+    if (!FRAME) {
+        // away from the frame the transposed stencil IS the forward blur (both kernels are symmetric) applied to gy:
+        // the packed-pair bodies of sharpen_kernel, then grad = alpha * gy + beta * blur(gy)
+        const f32x2 a2 = splat2(alpha), b2 = splat2(beta);
+#pragma unroll 1
+        for (int ch = 0; ch < 3; ++ch) {
+            f32x2 gc[2][2], bl[2][2], unused[2][2];
+            const float* pc = sm + ch * kSmH * kCpW + by * kCpW + bx + kColOff;
+            if (usm) usm_block2<false>(pc, sc, gc, bl, unused);
+            else box3_block2<false>(pc, 0u, gc, bl);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int gy = gy0 + r;
+                if (gy >= H) continue;
+                const f32x2 o0 = add2_sep(mul2(a2, gc[r][0]), mul2(b2, bl[r][0]));
+                const f32x2 o1 = add2_sep(mul2(a2, gc[r][1]), mul2(b2, bl[r][1]));
+                float* q = dst + ((size_t)ch * H + gy) * W + gx0;
+                if (vec_ok) {
+                    stg_stream4(q, make_float4(lo2(o0), hi2(o0), lo2(o1), hi2(o1)));
+                } else {
+                    const float o[4] = {lo2(o0), hi2(o0), lo2(o1), hi2(o1)};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (gx0 + i < W) q[i] = o[i];
+                }
+            }
+        }
+        return;
+    }
 #pragma unroll 1   // rolled: a third of the code (the unrolled kernel stalled on instruction fetch)
     for (int ch = 0; ch < 3; ++ch) {
         const float* pl = sm + ch * kSmH * kCpW + by * kCpW + bx + kColOff - 2;   // 8-byte aligned
